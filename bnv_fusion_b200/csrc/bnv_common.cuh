@@ -1,0 +1,106 @@
+// Shared declarations of libbnv_b200: device-side map layout, error plumbing, small helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bnv_b200.h"
+
+namespace bnv {
+
+constexpr int kFeat = 8;            // feature_vector_size (configs/model/fusion_pointnet_model.yaml:4)
+constexpr int kWidth = 64;          // n_neurons (src/models/tcnn_config.json:28)
+constexpr int32_t kEmpty = -1;      // slot-table sentinel
+constexpr double kFixScale = 1073741824.0;  // 2^30: fixed-point scale of the per-frame sums
+
+// latched device-side status bits
+constexpr int kErrCapacity = 1;     // value pool or frame scratch full
+constexpr int kErrRange = 2;        // key outside the grid
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define BNV_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) return bnv::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define BNV_LAUNCH_CHECK(name)                               \
+  do {                                                       \
+    bnv::count_launch();                                     \
+    cudaError_t _e = cudaGetLastError();                     \
+    if (_e != cudaSuccess) return bnv::cuda_fail(_e, name);  \
+  } while (0)
+
+// Geometry in the form the kernels consume.
+struct GeomDev {
+  float bmin[3];
+  float lo[3];          // bmin + (float)vs   (rule A1 bounds, fp32)
+  float hi[3];          // bmax - (float)vs
+  float vs;             // (float)voxel_size
+  float inv_vs;         // 1.0f / (float)voxel_size  (PyTorch-CUDA true-div fast path, rule A2)
+  int32_t n[3];
+  int32_t nyz;          // n[1]*n[2]
+  int64_t n_vox;
+  // tile shard (multi-GPU): owner(x) = (x >> brick_log2) % world
+  int32_t rank, world, brick_log2;
+};
+
+// Device-side view of the voxel map.
+struct MapDev {
+  GeomDev g;
+  // persistent map: flat id -> slot (identity-hashed table), dense SoA value pool in slot order
+  int32_t* table;       // [n_vox]
+  int32_t* keys;        // [cap] flat id of slot
+  float* feats;         // [cap, 8]
+  float* weights;       // [cap]
+  float* hits;          // [cap]
+  int32_t cap;
+  // per-frame scratch: flat id -> scratch row (the first (point,corner) row that touched the voxel)
+  int32_t* ftable;      // [n_vox]
+  int32_t* fkeys;       // [fcap]
+  long long* fsum;      // [fcap, 8] 2^30 fixed-point sums (order-independent => deterministic)
+  int32_t* fcnt;        // [fcap]
+  int32_t* touched;     // [fcap] scratch rows in first-touch order
+  int32_t fcap;
+  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] spare
+  int32_t* ctr;
+};
+
+__host__ __device__ inline bool owns(const GeomDev& g, int x) {
+  return g.world <= 1 || ((x >> g.brick_log2) % g.world) == g.rank;
+}
+
+}  // namespace bnv
+
+// The opaque handles of the C ABI.
+struct bnv_map {
+  bnv::MapDev d;
+  int device;
+  // scratch for the sorted encode_points path (CUB temp storage + index arrays)
+  void* cub_tmp;
+  size_t cub_tmp_bytes;
+  int32_t* sort_keys_in;
+  int32_t* sort_keys_out;
+  int32_t* sort_vals_in;
+  int32_t* sort_vals_out;
+  int32_t* flags;
+  int32_t* scan;
+  // dense back-projection staging for bnv_backproject
+  float* bp_pts;
+  int32_t* bp_flags;
+  int32_t* bp_scan;
+  int64_t max_points;
+  int64_t* stats;       // device int64[8] frame statistics accumulators
+};
+
+struct bnv_mlp {
+  int n_in, n_out, in_pad, out_pad, device;
+  int64_t n_params;
+  float* w32;           // device fp32 copy of params (row-major [out,in] blocks, as given)
+  void* w16;            // device fp16 image in the UMMA canonical shared-memory layout
+  size_t w16_bytes;
+};

@@ -1,0 +1,591 @@
+// Per-frame local fusion: back-projection, 8-neighbour expansion + encoder MLP + per-voxel
+// scatter-mean, running-average integration into the voxel map.
+//
+// Reference call chain being replaced (paths relative to the reference repo):
+//   src/datasets/fusion_inference_dataset.py:52-74  (depth -> world points + normals, CPU fp64)
+//   src/models/fusion/local_point_fusion.py:81-165  (encode_pointcloud, get_relative_xyz)
+//   src/models/fusion/modules.py:178-247            (get_neighbors)
+//   src/utils/pointnet_utils.py:283-294             (tcnn encoder forward)
+//   src/utils/voxel_utils.py:62-80                  (flatten / unflatten)
+//   torch.unique + torch_scatter.scatter_mean       (local_point_fusion.py:118-126)
+//   src/models/fusion/local_point_fusion.py:647-673 (_update / _integrate)
+//
+// Design: no sort and no per-row temporaries.  Every (point, corner) row looks its voxel up in the
+// per-frame identity table `ftable`; the first row to touch a voxel claims it with ONE atomicCAS
+// whose payload is the row's own index -- that index doubles as the voxel's scratch row, so no slot
+// allocator and no spinning are needed (the scratch arrays are as long as the frame's row count;
+// HBM capacity makes that free).  Features are accumulated as 2^30 fixed-point int64 atomics:
+// integer addition is associative, so the per-voxel mean is bit-reproducible regardless of the
+// order in which warps arrive (the reference's fp16 atomics are not).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "bnv_common.cuh"
+#include "bnv_mlp_simt.cuh"
+
+namespace bnv {
+
+struct Camera {
+  float fx, fy, cx, cy;   // float32 intrinsics as the dataset holds them
+  float T[12];            // float32 T_wc rows 0..2 (row-major 3x4)
+  double max_depth;
+  int H, W;
+};
+
+// masked metric depth of a pixel with replicate padding (load_depth, src/utils/common.py:93-112)
+__device__ __forceinline__ double depth_at(const uint16_t* __restrict__ d, const Camera& cam, int u, int v) {
+  u = min(max(u, 0), cam.W - 1);
+  v = min(max(v, 0), cam.H - 1);
+  const double z = (double)__ldg(d + (size_t)v * cam.W + u) / 1000.0;
+  return (z > 0.0 && z < cam.max_depth) ? z : 0.0;
+}
+
+// One pixel of FusionInferenceAbstractDataset.__getitem__ (fusion_inference_dataset.py:52-74) in
+// float64, rounded to float32 like run_e2e.py:247-249.  Op order == oracle/bnv_oracle.py.
+__device__ __forceinline__ bool backproject_pixel(const uint16_t* __restrict__ depth, const Camera& cam,
+                                                  int u, int v, float (&out)[6]) {
+  const double zc = depth_at(depth, cam, u, v);
+  if (!(zc > 0.0)) return false;
+  const double fx = (double)cam.fx, fy = (double)cam.fy, cx = (double)cam.cx, cy = (double)cam.cy;
+  // kornia depth_to_3d over the 3x3 neighbourhood (float64 (u-cx)/fx), Sobel/8, replicate pad
+  double X[3][3], Y[3][3], Z[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int uu = min(max(u + dx, 0), cam.W - 1), vv = min(max(v + dy, 0), cam.H - 1);
+      const double z = depth_at(depth, cam, uu, vv);
+      X[dy + 1][dx + 1] = __dmul_rn(__ddiv_rn(__dsub_rn((double)uu, cx), fx), z);
+      Y[dy + 1][dx + 1] = __dmul_rn(__ddiv_rn(__dsub_rn((double)vv, cy), fy), z);
+      Z[dy + 1][dx + 1] = z;
+    }
+  const double e = 0.125;
+  auto sobx = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[1][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[1][2]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  auto soby = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[0][1]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[2][1]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  const double gx0 = sobx(X), gx1 = sobx(Y), gx2 = sobx(Z);
+  const double gy0 = soby(X), gy1 = soby(Y), gy2 = soby(Z);
+  double n0 = __dsub_rn(__dmul_rn(gx1, gy2), __dmul_rn(gx2, gy1));
+  double n1 = __dsub_rn(__dmul_rn(gx2, gy0), __dmul_rn(gx0, gy2));
+  double n2 = __dsub_rn(__dmul_rn(gx0, gy1), __dmul_rn(gx1, gy0));
+  const double nn = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2)));
+  const double den = fmax(nn, 1e-12);
+  n0 = __ddiv_rn(n0, den); n1 = __ddiv_rn(n1, den); n2 = __ddiv_rn(n2, den);
+  // depth2xyz (src/utils/geometry.py:150-171): (u-cx)/fx in float32, then float64 * depth
+  const double xc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)u, cam.cx), cam.fx), zc);
+  const double yc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)v, cam.cy), cam.fy), zc);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double t0 = (double)cam.T[r * 4 + 0], t1 = (double)cam.T[r * 4 + 1], t2 = (double)cam.T[r * 4 + 2],
+                 t3 = (double)cam.T[r * 4 + 3];
+    const double p = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xc, t0), __dmul_rn(yc, t1)), __dmul_rn(zc, t2)), t3);
+    const double q = __dadd_rn(__dadd_rn(__dmul_rn(n0, t0), __dmul_rn(n1, t1)), __dmul_rn(n2, t2));
+    out[r] = (float)p;
+    out[3 + r] = (float)q;
+  }
+  return true;
+}
+
+// dense back-projection for bnv_backproject: all pixels + validity flags
+__global__ void backproject_kernel(const uint16_t* __restrict__ depth, Camera cam, float* __restrict__ pts,
+                                   int32_t* __restrict__ flags) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cam.H * cam.W) return;
+  float p[6];
+  const bool ok = backproject_pixel(depth, cam, idx % cam.W, idx / cam.W, p);
+  flags[idx] = ok ? 1 : 0;
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) pts[(size_t)idx * 6 + j] = p[j];
+  }
+}
+
+__global__ void compact_pts_kernel(const float* __restrict__ pts, const int32_t* __restrict__ flags,
+                                   const int32_t* __restrict__ scan, int n, float* __restrict__ out,
+                                   int32_t* __restrict__ n_valid) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  if (flags[idx]) {
+    const int o = scan[idx];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) out[(size_t)o * 6 + j] = pts[(size_t)idx * 6 + j];
+  }
+  if (idx == n - 1) *n_valid = scan[idx] + flags[idx];
+}
+
+// ------------------------------------------------------------------------------------------- //
+// encode: one thread per point, 8 corner rows each
+// ------------------------------------------------------------------------------------------- //
+using EncMlp = SimtMlp<6, 8>;
+constexpr int kEncThreads = 256;
+constexpr size_t kEncSmem = (size_t)(EncMlp::kFloats + 64 * kEncThreads) * sizeof(float);
+
+struct EncSrc {
+  const uint16_t* depth;   // FROM_DEPTH
+  Camera cam;
+  const float* pts6;       // !FROM_DEPTH
+  int64_t n_points;
+};
+
+__device__ __forceinline__ void scatter_row(const MapDev& m, int32_t flat, int32_t row, const float (&y)[8]) {
+  const int32_t old = atomicCAS(&m.ftable[flat], kEmpty, row);
+  const int32_t slot = old == kEmpty ? row : old;
+  if (old == kEmpty) {
+    m.fkeys[row] = flat;
+    const int32_t pos = atomicAdd(&m.ctr[1], 1);
+    m.touched[pos] = row;
+  }
+  atomicAdd(&m.fcnt[slot], 1);
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(m.fsum + (size_t)slot * kFeat);
+#pragma unroll
+  for (int j = 0; j < kFeat; ++j) {
+    const long long q = __double2ll_rn((double)y[j] * kFixScale);
+    atomicAdd(s + j, (unsigned long long)q);
+  }
+}
+
+template <bool FROM_DEPTH>
+__global__ void __launch_bounds__(kEncThreads) encode_simt_kernel(MapDev m, EncSrc src, const float* __restrict__ gW,
+                                                                  long long* __restrict__ stats) {
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;
+  float* sH = smem + EncMlp::kFloats + threadIdx.x;
+  load_weights(sW, gW, EncMlp::kFloats);
+  const int64_t idx = (int64_t)blockIdx.x * kEncThreads + threadIdx.x;
+  float p[6];
+  bool valid = false;
+  if (FROM_DEPTH) {
+    if (idx < (int64_t)src.cam.H * src.cam.W)
+      valid = backproject_pixel(src.depth, src.cam, (int)(idx % src.cam.W), (int)(idx / src.cam.W), p);
+  } else if (idx < src.n_points) {
+    valid = true;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
+  }
+  const GeomDev& g = m.g;
+  // rule A1 (local_point_fusion.py:94-100): strict bounds one voxel inside the volume
+  bool inb = valid;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) inb = inb && (p[a] < g.hi[a]) && (p[a] > g.lo[a]);
+  int n_rows = 0;
+  if (inb) {
+    float c[3], fl[3], ce[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      c[a] = __fmul_rn(__fsub_rn(p[a], g.bmin[a]), g.inv_vs);   // rule A2
+      fl[a] = floorf(c[a]);
+      ce[a] = ceilf(c[a]);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+      // corner order of get_neighbors (modules.py:178-247)
+      const int cx = (k == 1 || k == 4 || k == 5 || k == 7);
+      const int cy = (k == 2 || k == 4 || k == 6 || k == 7);
+      const int cz = (k == 3 || k == 5 || k == 6 || k == 7);
+      const float nb[3] = {cx ? ce[0] : fl[0], cy ? ce[1] : fl[1], cz ? ce[2] : fl[2]};
+      const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
+      if (!owns(g, ix)) continue;
+      float x[6], y[8];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float rel_n = __fsub_rn(c[a], nb[a]);              // rule A4
+        const float rel = __fmul_rn(rel_n, g.vs);
+        x[a] = __fmul_rn(rel, g.inv_vs);
+        x[3 + a] = p[3 + a];
+      }
+      EncMlp::run(sW, sH, kEncThreads, x, y);
+      const int32_t flat = ix * g.nyz + iy * g.n[2] + iz;       // rule A5 (int32)
+      scatter_row(m, flat, (int32_t)(idx * 8 + k), y);
+      ++n_rows;
+    }
+  }
+  // frame statistics: valid pixels / in-bounds points / rows
+  const unsigned mv = __ballot_sync(0xffffffffu, valid);
+  const unsigned mi = __ballot_sync(0xffffffffu, inb);
+  int r = n_rows;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  if ((threadIdx.x & 31) == 0 && (mv | mi)) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)__popc(mv));
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)r);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)__popc(mi));
+  }
+}
+
+// mean of a scratch row (scatter_mean, local_point_fusion.py:125)
+__device__ __forceinline__ float scratch_mean(const MapDev& m, int32_t row, int j, int32_t cnt) {
+  const long long s = m.fsum[(size_t)row * kFeat + j];
+  return (float)(((double)s / kFixScale) / (double)cnt);
+}
+
+// _update (local_point_fusion.py:647-651), separately rounded like the reference's torch kernels
+__device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new, float w_new, float w) {
+  return __fdiv_rn(__fadd_rn(__fmul_rn(f_old, w_old), __fmul_rn(f_new, w_new)), w);
+}
+
+// finalize of the fused path: for every voxel touched this frame -> mean, count filter, running
+// average into the persistent map; clears the scratch.  8 lanes per voxel (one feature each).
+__global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, long long* __restrict__ stats,
+                                                             long long* __restrict__ user_stats,
+                                                             float* __restrict__ user_navg) {
+  const int n_touched = m.ctr[1];
+  const int lane8 = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);   // the 8 lanes that share a voxel
+  int integrated = 0;
+  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_touched;
+       t += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int32_t row = m.touched[t];
+    const int32_t key = m.fkeys[row];
+    const int32_t cnt = m.fcnt[row];
+    const float mean = scratch_mean(m, row, lane8, cnt);
+    m.fsum[(size_t)row * kFeat + lane8] = 0;
+    if (cnt >= min_pts) {                                         // local_point_fusion.py:143-147
+      int32_t slot = 0;
+      if (lane8 == 0) {
+        slot = m.table[key];
+        if (slot < 0) {
+          slot = atomicAdd(&m.ctr[0], 1);
+          if (slot < m.cap) {
+            m.table[key] = slot;
+            m.keys[slot] = key;
+            m.weights[slot] = 0.f;
+            m.hits[slot] = 0.f;
+          } else {
+            atomicOr(&m.ctr[2], kErrCapacity);
+            slot = -1;
+          }
+          slot = slot < 0 ? -1 : (slot | 0x40000000);           // bit 30: freshly allocated
+        }
+      }
+      slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) & ~7);
+      if (slot >= 0) {
+        const bool fresh = slot & 0x40000000;
+        slot &= 0x3fffffff;
+        const float w_new = fminf(__fmul_rn((float)cnt, 0.03125f), 1.0f);   // clip(count/32, max=1)
+        const float w_old = fresh ? 0.f : m.weights[slot];
+        const float f_old = fresh ? 0.f : m.feats[(size_t)slot * kFeat + lane8];
+        const float w = __fadd_rn(w_old, w_new);
+        m.feats[(size_t)slot * kFeat + lane8] = fuse_feat(f_old, w_old, mean, w_new, w);
+        __syncwarp(gmask);
+        if (lane8 == 0) {
+          m.weights[slot] = w;
+          ++integrated;
+        }
+      }
+    }
+    if (lane8 == 0) {
+      m.ftable[key] = kEmpty;
+      m.fcnt[row] = 0;
+    }
+  }
+  if (integrated) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 3), (unsigned long long)integrated);
+  // last block publishes the frame statistics and re-arms the counters
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&m.ctr[3], 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    const long long rows = stats[1];
+    if (user_stats) {
+      user_stats[0] = stats[0];
+      user_stats[1] = rows;
+      user_stats[2] = n_touched;
+      user_stats[3] = *reinterpret_cast<volatile long long*>(stats + 3);
+    }
+    if (user_navg) *user_navg = n_touched > 0 ? (float)((double)rows / (double)n_touched) : 0.f;
+    stats[0] = stats[1] = stats[3] = stats[4] = 0;
+    m.ctr[1] = 0;
+    m.ctr[3] = 0;
+  }
+}
+
+// ---- sorted path (encode_pointcloud's return values) ----------------------------------------
+__global__ void sort_prep_kernel(MapDev m, int n, int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int32_t row = m.touched[t];
+  keys[t] = m.fkeys[row];
+  vals[t] = row;
+}
+
+__global__ void sort_flag_kernel(MapDev m, int n, const int32_t* __restrict__ rows, int min_pts,
+                                 int32_t* __restrict__ flags) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  flags[t] = m.fcnt[rows[t]] >= min_pts ? 1 : 0;
+}
+
+__global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ keys, const int32_t* __restrict__ rows,
+                                 const int32_t* __restrict__ flags, const int32_t* __restrict__ scan,
+                                 int64_t out_cap, float* __restrict__ feats, int64_t* __restrict__ counts,
+                                 int64_t* __restrict__ flat_ids, int64_t* __restrict__ coords) {
+  const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (int)(tt >> 3);
+  const int j = (int)(tt & 7);
+  if (t >= n) return;
+  const int32_t row = rows[t];
+  const int32_t key = keys[t];
+  const int32_t cnt = m.fcnt[row];
+  const float mean = scratch_mean(m, row, j, cnt);
+  m.fsum[(size_t)row * kFeat + j] = 0;
+  if (flags[t]) {
+    const int64_t o = scan[t];
+    if (o < out_cap) {
+      feats[o * kFeat + j] = mean;
+      if (j == 0) {
+        counts[o] = cnt;
+        flat_ids[o] = key;
+        const int32_t x = key / m.g.nyz;                          // unflatten, voxel_utils.py:68-80
+        const int32_t r = key - x * m.g.nyz;
+        const int32_t y = r / m.g.n[2];
+        coords[o * 3 + 0] = x;
+        coords[o * 3 + 1] = y;
+        coords[o * 3 + 2] = r - y * m.g.n[2];
+      }
+    } else if (j == 0) {
+      atomicOr(&m.ctr[2], kErrCapacity);
+    }
+  }
+  __syncwarp(0xFFu << ((threadIdx.x & 31) & ~7));
+  if (j == 0) {
+    m.ftable[key] = kEmpty;
+    m.fcnt[row] = 0;
+  }
+}
+
+__global__ void sort_publish_kernel(MapDev m, int n, const int32_t* __restrict__ flags, const int32_t* __restrict__ scan,
+                                    long long* __restrict__ stats, int64_t* __restrict__ user_stats,
+                                    float* __restrict__ user_navg) {
+  const long long M = n > 0 ? (long long)scan[n - 1] + flags[n - 1] : 0;
+  user_stats[0] = M;
+  user_stats[1] = n;
+  if (user_navg) *user_navg = n > 0 ? (float)((double)stats[1] / (double)n) : 0.f;
+  stats[0] = stats[1] = stats[3] = stats[4] = 0;
+  m.ctr[1] = 0;
+}
+
+// _integrate (local_point_fusion.py:653-673) on explicit arrays: 8 lanes per voxel
+__global__ void integrate_kernel(MapDev m, const int64_t* __restrict__ coords, const float* __restrict__ feats,
+                                 const int64_t* __restrict__ counts, int64_t n) {
+  const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = tt >> 3;
+  const int j = (int)(tt & 7);
+  const bool act = i < n;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  int32_t slot = -1;
+  if (act && j == 0) {
+    const long long x = coords[i * 3], y = coords[i * 3 + 1], z = coords[i * 3 + 2];
+    if (x < 0 || y < 0 || z < 0 || x >= m.g.n[0] || y >= m.g.n[1] || z >= m.g.n[2]) {
+      atomicOr(&m.ctr[2], kErrRange);
+    } else {
+      const int32_t flat = (int32_t)x * m.g.nyz + (int32_t)y * m.g.n[2] + (int32_t)z;
+      slot = m.table[flat];
+      if (slot == kEmpty) {
+        const int32_t tag = -(int32_t)(i % 0x3fffffff) - 2;
+        const int32_t old = atomicCAS(&m.table[flat], kEmpty, tag);
+        if (old == kEmpty) {
+          slot = atomicAdd(&m.ctr[0], 1);
+          if (slot < m.cap) {
+            m.keys[slot] = flat;
+            m.weights[slot] = 0.f;
+            m.hits[slot] = 0.f;
+            atomicExch(&m.table[flat], slot);
+            slot |= 0x40000000;
+          } else {
+            atomicOr(&m.ctr[2], kErrCapacity);
+            atomicExch(&m.table[flat], kEmpty);
+            slot = -1;
+          }
+        } else {
+          slot = old;   // negative tag: duplicate key in this call, the claimant integrates it
+        }
+      }
+    }
+  }
+  slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) & ~7);
+  if (!act || slot < 0) return;
+  const bool fresh = slot & 0x40000000;
+  slot &= 0x3fffffff;
+  const float w_new = fminf(__fmul_rn((float)counts[i], 0.03125f), 1.0f);
+  const float w_old = fresh ? 0.f : m.weights[slot];
+  const float f_old = fresh ? 0.f : m.feats[(size_t)slot * kFeat + j];
+  const float w = __fadd_rn(w_old, w_new);
+  m.feats[(size_t)slot * kFeat + j] = fuse_feat(f_old, w_old, feats[i * kFeat + j], w_new, w);
+  __syncwarp(gmask);
+  if (j == 0) m.weights[slot] = w;
+}
+
+static int make_camera(Camera& cam, int H, int W, const float* K, const float* T, double max_depth) {
+  if (!K || !T || H <= 0 || W <= 0) { set_error("camera: bad arguments"); return BNV_E_ARG; }
+  cam.fx = K[0]; cam.fy = K[4]; cam.cx = K[2]; cam.cy = K[5];
+  for (int i = 0; i < 12; ++i) cam.T[i] = T[i];
+  cam.max_depth = max_depth;
+  cam.H = H; cam.W = W;
+  return BNV_OK;
+}
+
+}  // namespace bnv
+
+using namespace bnv;
+
+// defined in bnv_mlp.cu / bnv_tc.cu
+const float* bnv_internal_simt_weights(const bnv_mlp_t* mlp);
+int bnv_internal_encode_tc(bnv_map_t* map, const void* src, int from_depth, int64_t n_threads,
+                           const bnv_mlp_t* enc, cudaStream_t s);
+
+namespace bnv {
+static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int64_t n_threads,
+                         const bnv_mlp_t* enc, int mode, cudaStream_t s) {
+  if (!enc || enc->n_in != 6 || enc->n_out != 8) { set_error("encode: encoder MLP must be 6 -> 8"); return BNV_E_ARG; }
+  if (n_threads > map->max_points) {
+    set_error("encode: %lld points exceed the map's max_points %lld", (long long)n_threads, (long long)map->max_points);
+    return BNV_E_CAPACITY;
+  }
+  if (n_threads == 0) return BNV_OK;
+  if (mode == BNV_MLP_TC16) return bnv_internal_encode_tc(map, &src, from_depth ? 1 : 0, n_threads, enc, s);
+  if (mode != BNV_MLP_FP32) { set_error("encode: unknown MLP mode %d", mode); return BNV_E_ARG; }
+  const unsigned blocks = (unsigned)((n_threads + kEncThreads - 1) / kEncThreads);
+  const float* gW = bnv_internal_simt_weights(enc);
+  if (from_depth) {
+    static bool attr = false;
+    if (!attr) { BNV_CUDA(cudaFuncSetAttribute(encode_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem)); attr = true; }
+    encode_simt_kernel<true><<<blocks, kEncThreads, kEncSmem, s>>>(map->d, src, gW, (long long*)map->stats);
+  } else {
+    static bool attr = false;
+    if (!attr) { BNV_CUDA(cudaFuncSetAttribute(encode_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem)); attr = true; }
+    encode_simt_kernel<false><<<blocks, kEncThreads, kEncSmem, s>>>(map->d, src, gW, (long long*)map->stats);
+  }
+  BNV_LAUNCH_CHECK("encode_simt_kernel");
+  return BNV_OK;
+}
+
+static int launch_finalize(bnv_map_t* map, int min_pts, int64_t* frame_stats, float* navg, cudaStream_t s) {
+  finalize_fused_kernel<<<148 * 2, 256, 0, s>>>(map->d, min_pts, (long long*)map->stats, (long long*)frame_stats, navg);
+  BNV_LAUNCH_CHECK("finalize_fused_kernel");
+  return BNV_OK;
+}
+}  // namespace bnv
+
+extern "C" {
+
+int bnv_backproject(bnv_map_t* map, const uint16_t* depth, int H, int W, const float* K, const float* T,
+                    double max_depth, float* pts6, int32_t* n_valid, void* stream) {
+  if (!map || !depth || !pts6 || !n_valid) { set_error("bnv_backproject: null argument"); return BNV_E_ARG; }
+  Camera cam;
+  int rc = make_camera(cam, H, W, K, T, max_depth);
+  if (rc) return rc;
+  const int n = H * W;
+  if (n > map->max_points) { set_error("bnv_backproject: %d pixels exceed max_points %lld", n, (long long)map->max_points); return BNV_E_CAPACITY; }
+  cudaStream_t s = (cudaStream_t)stream;
+  backproject_kernel<<<(n + 127) / 128, 128, 0, s>>>(depth, cam, map->bp_pts, map->bp_flags);
+  BNV_LAUNCH_CHECK("backproject_kernel");
+  size_t tmp = map->cub_tmp_bytes;
+  BNV_CUDA(cub::DeviceScan::ExclusiveSum(map->cub_tmp, tmp, map->bp_flags, map->bp_scan, n, s));
+  count_launch(2);
+  compact_pts_kernel<<<(n + 255) / 256, 256, 0, s>>>(map->bp_pts, map->bp_flags, map->bp_scan, n, pts6, n_valid);
+  BNV_LAUNCH_CHECK("compact_pts_kernel");
+  return BNV_OK;
+}
+
+int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const float* K, const float* T,
+                   double max_depth, const bnv_mlp_t* enc, int min_pts, int mode, int64_t* frame_stats,
+                   float* navg, void* stream) {
+  if (!map || !depth) { set_error("bnv_fuse_frame: null argument"); return BNV_E_ARG; }
+  EncSrc src{};
+  int rc = make_camera(src.cam, H, W, K, T, max_depth);
+  if (rc) return rc;
+  src.depth = depth;
+  cudaStream_t s = (cudaStream_t)stream;
+  rc = launch_encode(map, src, true, (int64_t)H * W, enc, mode, s);
+  if (rc) return rc;
+  return launch_finalize(map, min_pts, frame_stats, navg, s);
+}
+
+int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,
+                    int mode, int64_t* frame_stats, float* navg, void* stream) {
+  if (!map || n_points < 0 || (n_points > 0 && !pts6)) { set_error("bnv_fuse_points: bad argument"); return BNV_E_ARG; }
+  EncSrc src{};
+  src.pts6 = pts6;
+  src.n_points = n_points;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_encode(map, src, false, n_points, enc, mode, s);
+  if (rc) return rc;
+  return launch_finalize(map, min_pts, frame_stats, navg, s);
+}
+
+int bnv_encode_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,
+                      int mode, float* feats, int64_t* counts, int64_t* flat_ids, int64_t* coords,
+                      int64_t out_capacity, int64_t* stats_dev, float* navg_dev, void* stream) {
+  if (!map || n_points < 0 || !stats_dev || (n_points > 0 && !pts6) ||
+      (out_capacity > 0 && (!feats || !counts || !flat_ids || !coords))) {
+    set_error("bnv_encode_points: bad argument");
+    return BNV_E_ARG;
+  }
+  EncSrc src{};
+  src.pts6 = pts6;
+  src.n_points = n_points;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_encode(map, src, false, n_points, enc, mode, s);
+  if (rc) return rc;
+  // The reference synchronises here as well (torch.unique's output size, `int(v) for v in n_xyz`,
+  // local_point_fusion.py:90,118): the sorted path reads the touched-voxel count to size the sort.
+  int32_t c[4];
+  BNV_CUDA(cudaMemcpyAsync(c, map->d.ctr, sizeof(c), cudaMemcpyDeviceToHost, s));
+  BNV_CUDA(cudaStreamSynchronize(s));
+  const int n = c[1];
+  if (n > 0) {
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    sort_prep_kernel<<<nb, 256, 0, s>>>(map->d, n, map->sort_keys_in, map->sort_vals_in);
+    BNV_LAUNCH_CHECK("sort_prep_kernel");
+    size_t tmp = map->cub_tmp_bytes;
+    int end_bit = 1;
+    while (end_bit < 31 && (1ll << end_bit) < map->d.g.n_vox) ++end_bit;
+    BNV_CUDA(cub::DeviceRadixSort::SortPairs(map->cub_tmp, tmp, map->sort_keys_in, map->sort_keys_out,
+                                             map->sort_vals_in, map->sort_vals_out, n, 0, end_bit, s));
+    count_launch(4);
+    sort_flag_kernel<<<nb, 256, 0, s>>>(map->d, n, map->sort_vals_out, min_pts, map->flags);
+    BNV_LAUNCH_CHECK("sort_flag_kernel");
+    tmp = map->cub_tmp_bytes;
+    BNV_CUDA(cub::DeviceScan::ExclusiveSum(map->cub_tmp, tmp, map->flags, map->scan, n, s));
+    count_launch(2);
+    sort_emit_kernel<<<(unsigned)(((int64_t)n * 8 + 255) / 256), 256, 0, s>>>(
+        map->d, n, map->sort_keys_out, map->sort_vals_out, map->flags, map->scan, out_capacity, feats, counts,
+        flat_ids, coords);
+    BNV_LAUNCH_CHECK("sort_emit_kernel");
+  }
+  sort_publish_kernel<<<1, 1, 0, s>>>(map->d, n, map->flags, map->scan, (long long*)map->stats, stats_dev, navg_dev);
+  BNV_LAUNCH_CHECK("sort_publish_kernel");
+  if (n > 0) {
+    // flags are reused by count_optim as a zero-initialised mark array
+    BNV_CUDA(cudaMemsetAsync(map->flags, 0, (size_t)n * 4, s));
+  }
+  return BNV_OK;
+}
+
+int bnv_integrate(bnv_map_t* map, const int64_t* coords, const float* feats, const int64_t* counts, int64_t n,
+                  void* stream) {
+  if (!map || n < 0 || (n > 0 && (!coords || !feats || !counts))) { set_error("bnv_integrate: bad argument"); return BNV_E_ARG; }
+  if (n == 0) return BNV_OK;
+  integrate_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(map->d, coords, feats, counts, n);
+  BNV_LAUNCH_CHECK("integrate_kernel");
+  return BNV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+/* bnv_b200.h -- C ABI of libbnv_b200.so: BNV-Fusion's per-frame dense hot path on B200 (sm_100a).
+ *
+ * The reference (likojack/bnv_fusion, pure Python) has no FFI of its own; this is the boundary a
+ * maintainer binds with ctypes to replace the third-party native code the
+ * path runs on today (tinycudann, torch_scatter, open3d.core.HashMap, torch.unique, grid_sample,
+ * kornia).  Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repo root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every `dev` pointer is device memory owned by the caller
+ *     (e.g. torch.Tensor.data_ptr()), every `host` pointer is ordinary host memory.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and never synchronise the host unless stated ("host sync").
+ *   - return 0 on success, a negative BNV_E* code otherwise; bnv_last_error() gives the message
+ *     (thread-local).  Device-side faults that cannot be reported synchronously (capacity
+ *     overflow, key outside the grid) are latched in the map and returned by bnv_map_status().
+ *   - float maths follows the op order PyTorch-CUDA executes for the reference (SURVEY.md §8a
+ *     rules A1-A8 / D1-D7), in particular `tensor / python_scalar` == x * (1.0f / (float)s).
+ */
+#ifndef BNV_B200_H
+#define BNV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNV_ABI_VERSION 1
+
+#define BNV_OK 0
+#define BNV_E_ARG (-1)      /* bad argument */
+#define BNV_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError_t string) */
+#define BNV_E_CAPACITY (-3) /* a fixed-capacity buffer would overflow */
+#define BNV_E_RANGE (-4)    /* voxel key outside the grid */
+#define BNV_E_ALLOC (-5)    /* out of memory */
+#define BNV_E_UNSUPPORTED (-6)
+
+/* MLP arithmetic selector for bnv_mlp_create / the encode and decode calls. */
+#define BNV_MLP_FP32 0 /* fp32 CUDA-core path: the exact-parity mode (fp32 oracle, ~1e-6) */
+#define BNV_MLP_TC16 1 /* tcgen05 tensor-core path: fp16 operands, fp32 accumulators in TMEM */
+
+typedef struct bnv_map bnv_map_t; /* sparse voxel map  == reference SparseVolume */
+typedef struct bnv_mlp bnv_mlp_t; /* packed weights of one tiny MLP == tcnn.NetworkWithInputEncoding */
+
+/* Geometry of the voxel grid (reference: SparseVolume.__init__, src/models/sparse_volume.py:485-497,
+ * voxel_utils.get_world_range, src/utils/voxel_utils.py:83-88).  bmin/bmax are the float32-cast
+ * world bounds, voxel_size the Python double the reference passes around. */
+typedef struct bnv_geom {
+  float bmin[3];
+  float bmax[3];
+  double voxel_size;
+  int32_t n_xyz[3];
+} bnv_geom_t;
+
+int bnv_abi_version(void);
+const char* bnv_last_error(void);
+
+/* ---- tiny MLPs ------------------------------------------------------------------------------
+ * Replaces tcnn.NetworkWithInputEncoding(Identity -> FullyFusedMLP, 64 neurons, 3 hidden layers,
+ * ReLU, no bias) constructed at src/utils/pointnet_utils.py:274-279 (encoder, 6 -> 8) and
+ * src/models/fusion/modules.py:171-176 (decoder, 17 -> 1).  `params_host` is the flat float32
+ * `model.params` tensor of the checkpoint (10240 / 11264 floats): [W0 | W1 | W2 | W3], each block
+ * row-major [out, in], input padded with ones to a multiple of 16 (tiny-cuda-nn semantics). */
+int bnv_mlp_create(bnv_mlp_t** out, const float* params_host, int64_t n_params, int n_in, int n_out,
+                   int device);
+int bnv_mlp_destroy(bnv_mlp_t* mlp);
+/* Plain batched forward (tcnnPointNetEncoder.forward, pointnet_utils.py:283-294;
+ * tcnnNeRFModel.geo_forward, modules.py:249-253).  x_dev [n, n_in] fp32 -> y_dev [n, n_out] fp32. */
+int bnv_mlp_forward(const bnv_mlp_t* mlp, const float* x_dev, int64_t n, float* y_dev, int mode,
+                    void* stream);
+
+/* ---- sparse voxel map -----------------------------------------------------------------------
+ * Replaces SparseVolume over open3d.core.HashMap (src/models/sparse_volume.py:484-600).  Keys are
+ * voxel coordinates (x,y,z) inside the grid; the reference's int32 flat id
+ * (voxel_utils.flatten, src/utils/voxel_utils.py:62-65) is < 2^31 by construction, so the map uses
+ * the flat id itself as a collision-free index into an HBM-resident slot table.
+ * `capacity` = rows of the value pool (active voxels), `max_points` = most points one frame may
+ * carry (sizes the per-frame accumulators: 8 rows per point). */
+int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t capacity,
+                   int64_t max_points, int device);
+int bnv_map_destroy(bnv_map_t* map);
+/* Drop all voxels (SparseVolume.reset, sparse_volume.py:587-600). */
+int bnv_map_reset(bnv_map_t* map, void* stream);
+/* Number of active voxels and latched device-side status.  Host sync on `stream`. */
+int bnv_map_size(bnv_map_t* map, int64_t* n_active_host, void* stream);
+int bnv_map_status(bnv_map_t* map, void* stream);
+/* Tile ownership for the multi-GPU shard: a voxel belongs to rank ((x >> brick_log2) % world).
+ * Encode calls drop (point, corner) rows whose voxel another rank owns.  world = 1 disables. */
+int bnv_map_set_shard(bnv_map_t* map, int rank, int world, int brick_log2);
+
+/* SparseVolume.query (sparse_volume.py:661-695): coords_dev [n,3] int64 -> feats [n,F], weights [n],
+ * num_hits [n] (zeros for misses), found [n] uint8 (nullable). */
+int bnv_map_query(bnv_map_t* map, const int64_t* coords_dev, int64_t n, float* feats_dev,
+                  float* weights_dev, float* hits_dev, uint8_t* found_dev, void* stream);
+/* SparseVolume.insert (sparse_volume.py:561-585): upsert -- insert absent keys, overwrite all three
+ * values of present ones.  Duplicate keys inside one call: one of them wins (as with o3c). */
+int bnv_map_insert(bnv_map_t* map, const int64_t* coords_dev, const float* feats_dev,
+                   const float* weights_dev, const float* hits_dev, int64_t n, void* stream);
+/* SparseVolume.to_tensor (sparse_volume.py:525-559): copy the first n active rows (n from
+ * bnv_map_size) to dense tensors.  Row r of the export is the map's slot r; the decode calls use
+ * that identity instead of the reference's second hash map (tensor_indexer). */
+int bnv_map_export(bnv_map_t* map, int64_t n, int64_t* coords_dev, float* feats_dev,
+                   float* weights_dev, float* hits_dev, void* stream);
+/* SparseVolume.count_optim (sparse_volume.py:602-622): weights_rows[row(key)] += 1 for every key
+ * found among the first n_rows slots (non-accumulating for duplicate keys, like index_put). */
+int bnv_map_count_optim(bnv_map_t* map, const float* nbr_coords_dev, int64_t n, float* weights_rows_dev,
+                        int64_t n_rows, void* stream);
+
+/* ---- per-frame local fusion -----------------------------------------------------------------
+ * bnv_backproject: the dataset-side arithmetic of FusionInferenceAbstractDataset.__getitem__
+ * (src/datasets/fusion_inference_dataset.py:52-74; load_depth, src/utils/common.py:86-120;
+ * depth2xyz, src/utils/geometry.py:150-171; kornia depth_to_normals) in float64 on the device,
+ * rounded to float32 like run_e2e.py:247-249.  depth_mm_dev [H,W] uint16 millimetres; K_host [9]
+ * and T_wc_host [16] row-major float32.  Writes the masked pixels' [x,y,z,nx,ny,nz] in row-major
+ * pixel order to pts6_dev [H*W,6] and their number to n_valid_dev. */
+int bnv_backproject(bnv_map_t* map, const uint16_t* depth_mm_dev, int H, int W, const float* K_host,
+                    const float* T_wc_host, double max_depth, float* pts6_dev, int32_t* n_valid_dev,
+                    void* stream);
+
+/* LitFusionPointNet.encode_pointcloud(..., return_dense=False)
+ * (src/models/fusion/local_point_fusion.py:81-151): bound mask, 8-neighbour expansion, encoder MLP
+ * per (point, corner) row, per-voxel mean, count >= min_pts filter, ascending flat-id order.
+ * Outputs sized for `out_capacity` voxels: feats [cap,F] f32, counts [cap] i64, flat_ids [cap] i64,
+ * coords [cap,3] i64; stats_dev int64[2] = {M (voxels written), M_t (touched voxels)};
+ * navg_dev float = mean points per touched voxel.  M == 0 and M_t == 0 <=> the reference returns
+ * five Nones. */
+int bnv_encode_points(bnv_map_t* map, const float* pts6_dev, int64_t n_points, const bnv_mlp_t* enc,
+                      int min_pts, int mode, float* feats_dev, int64_t* counts_dev,
+                      int64_t* flat_ids_dev, int64_t* coords_dev, int64_t out_capacity,
+                      int64_t* stats_dev, float* navg_dev, void* stream);
+
+/* LitFusionPointNet._integrate / _update (local_point_fusion.py:647-673): weight = clip(count/32,1),
+ * running weighted mean with the stored voxel, upsert (num_hits written back unchanged). */
+int bnv_integrate(bnv_map_t* map, const int64_t* coords_dev, const float* feats_dev,
+                  const int64_t* counts_dev, int64_t n, void* stream);
+
+/* The whole of NeuralMap.integrate's local-fusion half (src/run_e2e.py:78-98) for one depth frame
+ * in two kernels and no intermediate tensors: back-project -> encode -> integrate.  Leaves the map
+ * in the same state as bnv_backproject + bnv_encode_points + bnv_integrate.  frame_stats_dev
+ * (nullable) int64[4] = {valid pixels, rows, touched voxels, voxels integrated}; navg_dev nullable. */
+int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth_mm_dev, int H, int W, const float* K_host,
+                   const float* T_wc_host, double max_depth, const bnv_mlp_t* enc, int min_pts,
+                   int mode, int64_t* frame_stats_dev, float* navg_dev, void* stream);
+/* Same, starting from world-space points (frame['input_pts'], [n,6] fp32). */
+int bnv_fuse_points(bnv_map_t* map, const float* pts6_dev, int64_t n_points, const bnv_mlp_t* enc,
+                    int min_pts, int mode, int64_t* frame_stats_dev, float* navg_dev, void* stream);
+
+/* ---- SDF decode -----------------------------------------------------------------------------
+ * SparseVolume.decode_pts (src/models/sparse_volume.py:768-833) with fusion/utils.get_neighbors
+ * (src/models/fusion/utils.py:98-167), positional_encoding (src/models/fusion/modules.py:81-123),
+ * tcnnNeRFModel.geo_forward (modules.py:249-253), _query_tensor (sparse_volume.py:625-659) and the
+ * nearest-neighbour grid_sample of the TSDF prior (sparse_volume.py:819-832) fused into one kernel.
+ * coords_dev [Q,3] fp32 (voxel units if is_coords, else world); feats_rows/weights_rows are the
+ * exported (possibly optimised) tensors of bnv_map_export with n_rows rows; tsdf_delta_dev nullable
+ * [Tx,Ty,Tz] fp32.  out_sdf_dev [Q]; out_mask_dev [Q] uint8 nullable. */
+int bnv_decode_sdf(bnv_map_t* map, const float* coords_dev, int64_t n_queries, int is_coords,
+                   const float* feats_rows_dev, const float* weights_rows_dev, int64_t n_rows,
+                   const bnv_mlp_t* dec, int min_pts, int mode, const float* tsdf_delta_dev,
+                   const int32_t* tsdf_dims_host, float* out_sdf_dev, uint8_t* out_mask_dev,
+                   void* stream);
+/* The sampling half of SparseVolume.meshlize (sparse_volume.py:697-738) fused with the decode:
+ * for active voxels [first, first+count) evaluate the 27 samples id + {-0.5,0,0.5}^3.
+ * out_sdf_dev [count,27] ('ij' meshgrid order). */
+int bnv_decode_voxel_blocks(bnv_map_t* map, int64_t first, int64_t count, const float* feats_rows_dev,
+                            const float* weights_rows_dev, int64_t n_rows, const bnv_mlp_t* dec,
+                            int min_pts, int mode, const float* tsdf_delta_dev,
+                            const int32_t* tsdf_dims_host, float* out_sdf_dev, void* stream);
+
+/* Number of kernels this library launched since load (bench.py's gpu_launches evidence). */
+int64_t bnv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNV_B200_H */

@@ -1,0 +1,48 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/bnv_b200.h
+declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+from bnv_fusion_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "bnv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_header_symbols():
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/bnv_b200.h but not exported"
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+
+
+def test_abi_version_and_error_string():
+    lib = _lib.load()
+    assert lib.bnv_abi_version() == 1
+    assert isinstance(lib.bnv_last_error(), bytes)
+    assert lib.bnv_launch_count() >= 0
+
+
+def test_bad_arguments_fail_loudly_without_gpu():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.bnv_map_create(ctypes.byref(h), None, 8, 1024, 1024, 0)
+    assert rc == -1 and b"null" in lib.bnv_last_error()
+    rc = lib.bnv_mlp_create(ctypes.byref(h), None, 0, 6, 8, 0)
+    assert rc == -1
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
