@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- BNV-Fusion per-frame dense hot path on B200.
+
+A "step" is one pass of the hot path over one 640x480 synthetic depth frame of the `lounge`
+workload (BASELINE.json configs[1] shape: K = (525,525,319.5,239.5), 1 cm voxels, 5.1 m cube ->
+512^3 sparse grid): back-projection -> 8-neighbour expansion + encoder MLP + per-voxel scatter-mean
+-> running-average integration into the voxel map (NeuralMap.integrate's local-fusion half,
+/root/reference/src/run_e2e.py:78-98).
+
+  value      frames/s, depth frames resident in HBM, CUDA-event time per step, L2 flushed between
+             steps (cold-cache, conservative);  `value_warm` = same steps back to back, no flush
+  e2e        frames/s through the public API with HOST buffers: pinned uint16 depth -> H2D copy ->
+             fuse -> D2H read of the frame statistics, every step
+  roofline   dominant kernel (the fused encode kernel) against the measured bf16 tensor peak, and
+             the decode kernel's roofline under "decode" (SDF-decode Mqueries/s, the second half of
+             BASELINE.json's metric)
+  cpu_baseline  the numpy oracle port of the same path on the host cores (bounded sample)
+
+`--impl reference` times the reference algorithm's CPU implementation (the oracle port; the
+reference itself is Python that needs packages absent from this image) on the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENC_FLOP_PER_ROW = 2 * (6 * 64 + 64 * 64 + 64 * 64 + 64 * 8)         # 18 176
+DEC_FLOP_PER_QUERY = 8 * 2 * (17 * 64 + 64 * 64 + 64 * 64 + 64 * 1)  # 149 504
+N_FRAMES = 16
+WORKLOAD = "lounge"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_frames(n):
+    from bnv_fusion_b200 import synth
+    spec = synth.stream_spec(WORKLOAD)
+    return spec, [synth.make_frame(spec, i, seed=0) for i in range(n)]
+
+
+# --------------------------------------------------------------------------------------------- #
+def oracle_frame(O, grid, vm, enc, d, K, T, max_depth, rows=None):
+    if rows is not None:                      # bounded sample: the first `rows` image rows
+        d = d[:rows]
+    depth, mask = O.load_depth_u16(d, max_depth)
+    pts6 = O.backproject(depth, mask, K, T)
+    feats, counts, flat, coords, navg, _ = O.encode_pointcloud(pts6, grid, enc, 8)
+    O.integrate(vm, flat, feats, counts)
+    return 0 if flat is None else len(flat)
+
+
+def cpu_port(spec, frames, n_steps, sample_rows):
+    """The oracle port of the hot path on the host cores; value scaled to whole frames/s."""
+    from oracle import bnv_oracle as O
+    p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vm = O.VoxelMap(grid)
+    d, K, T = frames[0]
+    oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=8)       # warm BLAS
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        d, K, T = frames[i % len(frames)]
+        oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=sample_rows)
+    dt = (time.perf_counter() - t0) / n_steps
+    scale = spec.height / sample_rows
+    return 1.0 / (dt * scale), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec, frames = make_frames(4)
+    sample_rows = 60
+    steps = max(1, args.steps)
+    for _ in range(min(args.warmup, 1)):
+        cpu_port(spec, frames, 1, sample_rows)
+    fps, dt = cpu_port(spec, frames, steps, sample_rows)
+    cores = os.cpu_count()
+    sample = f"{sample_rows} of {spec.height} image rows per step (x{spec.height // sample_rows} scaled), numpy oracle port, BLAS threads <= {cores}"
+    print(json.dumps({
+        "impl": "reference", "metric": "fusion_frames_per_sec", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (spec.height / sample_rows),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "lounge 640x480 depth, 1 cm voxels, 512^3 sparse grid, per-frame local fusion"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------- #
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from bnv_fusion_b200 import _lib, config
+    from bnv_fusion_b200.model import LitFusionPointNet
+    from bnv_fusion_b200.volume import SparseVolume
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if args.mlp:
+        config.set_mlp_mode(args.mlp)
+    lib = _lib.load()
+    pk = peaks()
+
+    spec, frames = make_frames(N_FRAMES)
+    p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
+    cfg = {"trainer": {"dense_volume": False},
+           "model": {"feature_vector_size": 8, "voxel_size": spec.voxel_size, "min_pts_in_grid": 8,
+                     "point_net": {"in_channels": 6}, "nerf": {"num_encoding_fn_xyz": 1}}}
+    model = LitFusionPointNet(cfg)
+    # pretrained/pointnet_tcnn.ckpt tensors (shipped as a test fixture); random-init would time the same
+    model.load_state_dict({"pointnet_backbone.model.params": torch.from_numpy(p["encoder"]),
+                           "nerf.model.params": torch.from_numpy(p["decoder"])})
+    model.eval(); model.cuda(); model.freeze()
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    if world > 1:
+        vol.set_shard(rank, world, 4)
+    H, W = spec.height, spec.width
+    host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
+    devf = [h.to(dev).view(torch.uint16) for h in host]
+    stage = torch.empty((H, W), dtype=torch.int16, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step(i, from_host=False):
+        _, K, T = frames[i % N_FRAMES]
+        if from_host:
+            stage.copy_(host[i % N_FRAMES], non_blocking=True)
+            model.fuse_depth_frame(vol, stage.view(torch.uint16), K, T, spec.max_depth, stats=stats)
+            stats_host.copy_(stats, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the user reads the frame's result
+        else:
+            model.fuse_depth_frame(vol, devf[i % N_FRAMES], K, T, spec.max_depth, stats=stats)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    # ---- device-resident, L2 flushed between steps; per-kernel events for the roofline ---------
+    lib.bnv_map_set_timing(vol._handle, 1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.bnv_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    enc_ms, fin_ms, rows_total = [], [], 0
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(args.warmup + i)
+        ev[i][1].record()
+        a, b = C.c_float(), C.c_float()
+        _lib.check(lib.bnv_map_get_timing(vol._handle, C.byref(a), C.byref(b)), "timing")
+        enc_ms.append(a.value); fin_ms.append(b.value)
+        rows_total += int(stats[1])
+    barrier()
+    launches = lib.bnv_launch_count() - launches0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    lib.bnv_map_set_timing(vol._handle, 0)
+    # ---- same steps back to back (warm L2), one event pair ------------------------------------
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + args.steps + i)
+    e1.record()
+    barrier()
+    warm_ms = e0.elapsed_time(e1) / args.steps
+    # ---- end to end through the public API with host buffers ----------------------------------
+    for i in range(2):
+        step(i, from_host=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(2 * args.steps + i, from_host=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop()
+    vol.check_status()
+
+    # ---- decode: 27 samples per active voxel, repeated to >= 10 M queries ----------------------
+    vol.to_tensor()
+    A = vol.active_coordinates.shape[0]
+    vol.weights += 8.0              # every voxel "valid": the MLP runs for all corners regardless (rule D7)
+    reps = max(1, int(np.ceil(10_000_000 / max(A * 27, 1))))
+    vol.decode_voxel_blocks(model.nerf)
+    torch.cuda.synchronize()
+    dq = []
+    for _ in range(3):
+        flush.zero_()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(reps):
+            vol.decode_voxel_blocks(model.nerf)
+        d1.record()
+        torch.cuda.synchronize()
+        dq.append(d0.elapsed_time(d1))
+    dec_ms = float(np.median(dq))
+    n_q = A * 27 * reps
+    dec_tflops = DEC_FLOP_PER_QUERY * n_q / (dec_ms * 1e-3) / 1e12
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = maxr(float(np.sum(step_ms))) / args.steps
+    warm_ms, e2e_ms = maxr(warm_ms), maxr(e2e_ms)
+    enc_avg = float(np.mean(enc_ms))
+    rows_per_launch = rows_total / args.steps
+    enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        fps, dt = cpu_port(spec, frames, 2, 60)
+        cpu = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "2 steps of 60/480 image rows (x8 scaled) through oracle/bnv_oracle.py (numpy, float64 MLP)"}
+    if rank == 0:
+        out = {
+            "metric": "fusion_frames_per_sec", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "lounge 640x480 depth, 1 cm voxels, 512^3 sparse grid, per-frame local fusion "
+                                   "(backproject+encode+integrate), pretrained pointnet_tcnn weights",
+                       "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
+                       "parallelism": "1 GPU" if world == 1 else f"x-brick tile shard over {world} GPUs"},
+            "value_warm": 1e3 / warm_ms,
+            "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "encode (fused backproject + 8-corner MLP + scatter)", "bound": "tensor",
+                         "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                         "frac": enc_tflops / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
+                         "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "finalize_ms": float(np.mean(fin_ms))},
+            "decode": {"value": n_q / (dec_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_q, "active_voxels": A,
+                       "ms": dec_ms,
+                       "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                                    "frac": dec_tflops / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"]}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

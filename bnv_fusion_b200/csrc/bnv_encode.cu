@@ -513,9 +513,13 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   if (rc) return rc;
   src.depth = depth;
   cudaStream_t s = (cudaStream_t)stream;
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
   rc = launch_encode(map, src, true, (int64_t)H * W, enc, mode, s);
   if (rc) return rc;
-  return launch_finalize(map, min_pts, frame_stats, navg, s);
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
+  rc = launch_finalize(map, min_pts, frame_stats, navg, s);
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[2], s));
+  return rc;
 }
 
 int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,
@@ -525,9 +529,13 @@ int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const b
   src.pts6 = pts6;
   src.n_points = n_points;
   cudaStream_t s = (cudaStream_t)stream;
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
   int rc = launch_encode(map, src, false, n_points, enc, mode, s);
   if (rc) return rc;
-  return launch_finalize(map, min_pts, frame_stats, navg, s);
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
+  rc = launch_finalize(map, min_pts, frame_stats, navg, s);
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[2], s));
+  return rc;
 }
 
 int bnv_encode_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,

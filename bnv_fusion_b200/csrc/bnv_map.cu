@@ -258,6 +258,7 @@ int bnv_map_destroy(bnv_map_t* m) {
                   m->sort_vals_out, m->flags, m->scan, m->bp_pts, m->bp_flags, m->bp_scan, m->stats,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   delete m;
   return BNV_OK;
 }
@@ -297,6 +298,23 @@ int bnv_map_set_shard(bnv_map_t* m, int rank, int world, int brick_log2) {
     return BNV_E_ARG;
   }
   m->d.g.rank = rank; m->d.g.world = world; m->d.g.brick_log2 = brick_log2;
+  return BNV_OK;
+}
+
+int bnv_map_set_timing(bnv_map_t* m, int enable) {
+  if (!m) { set_error("bnv_map_set_timing: null map"); return BNV_E_ARG; }
+  BNV_CUDA(cudaSetDevice(m->device));
+  if (enable && !m->ev[0])
+    for (int i = 0; i < 3; ++i) BNV_CUDA(cudaEventCreate(&m->ev[i]));
+  m->timing = enable ? 1 : 0;
+  return BNV_OK;
+}
+
+int bnv_map_get_timing(bnv_map_t* m, float* enc_ms, float* fin_ms) {
+  if (!m || !m->ev[0] || !enc_ms || !fin_ms) { set_error("bnv_map_get_timing: timing was never enabled"); return BNV_E_ARG; }
+  BNV_CUDA(cudaEventSynchronize(m->ev[2]));
+  BNV_CUDA(cudaEventElapsedTime(enc_ms, m->ev[0], m->ev[1]));
+  BNV_CUDA(cudaEventElapsedTime(fin_ms, m->ev[1], m->ev[2]));
   return BNV_OK;
 }
 

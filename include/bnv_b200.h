@@ -168,6 +168,12 @@ int bnv_decode_voxel_blocks(bnv_map_t* map, int64_t first, int64_t count, const 
                             int min_pts, int mode, const float* tsdf_delta_dev,
                             const int32_t* tsdf_dims_host, float* out_sdf_dev, void* stream);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, bnv_fuse_frame / bnv_fuse_points
+ * record CUDA events on `stream` around the encode kernel and the finalize kernel.
+ * bnv_map_get_timing waits for the last recorded call (host sync) and returns both durations. */
+int bnv_map_set_timing(bnv_map_t* map, int enable);
+int bnv_map_get_timing(bnv_map_t* map, float* encode_ms_host, float* finalize_ms_host);
+
 /* Number of kernels this library launched since load (bench.py's gpu_launches evidence). */
 int64_t bnv_launch_count(void);
 
