@@ -1,0 +1,108 @@
+// Per-frame device helpers shared by the CUDA-core and tcgen05 encode kernels: camera model,
+// float64 back-projection of one pixel, scatter of one encoded row into the per-frame accumulators.
+#pragma once
+#include "bnv_common.cuh"
+
+namespace bnv {
+
+struct Camera {
+  float fx, fy, cx, cy;   // float32 intrinsics as the dataset holds them
+  float T[12];            // float32 T_wc rows 0..2 (row-major 3x4)
+  double max_depth;
+  int H, W;
+};
+
+// masked metric depth of a pixel with replicate padding (load_depth, src/utils/common.py:93-112)
+__device__ __forceinline__ double depth_at(const uint16_t* __restrict__ d, const Camera& cam, int u, int v) {
+  u = min(max(u, 0), cam.W - 1);
+  v = min(max(v, 0), cam.H - 1);
+  const double z = (double)__ldg(d + (size_t)v * cam.W + u) / 1000.0;
+  return (z > 0.0 && z < cam.max_depth) ? z : 0.0;
+}
+
+// One pixel of FusionInferenceAbstractDataset.__getitem__ (fusion_inference_dataset.py:52-74) in
+// float64, rounded to float32 like run_e2e.py:247-249.  Op order == oracle/bnv_oracle.py.
+__device__ __forceinline__ bool backproject_pixel(const uint16_t* __restrict__ depth, const Camera& cam,
+                                                  int u, int v, float (&out)[6]) {
+  const double zc = depth_at(depth, cam, u, v);
+  if (!(zc > 0.0)) return false;
+  const double fx = (double)cam.fx, fy = (double)cam.fy, cx = (double)cam.cx, cy = (double)cam.cy;
+  // kornia depth_to_3d over the 3x3 neighbourhood (float64 (u-cx)/fx), Sobel/8, replicate pad
+  double X[3][3], Y[3][3], Z[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int uu = min(max(u + dx, 0), cam.W - 1), vv = min(max(v + dy, 0), cam.H - 1);
+      const double z = depth_at(depth, cam, uu, vv);
+      X[dy + 1][dx + 1] = __dmul_rn(__ddiv_rn(__dsub_rn((double)uu, cx), fx), z);
+      Y[dy + 1][dx + 1] = __dmul_rn(__ddiv_rn(__dsub_rn((double)vv, cy), fy), z);
+      Z[dy + 1][dx + 1] = z;
+    }
+  const double e = 0.125;
+  auto sobx = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[1][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[1][2]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  auto soby = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[0][1]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[2][1]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  const double gx0 = sobx(X), gx1 = sobx(Y), gx2 = sobx(Z);
+  const double gy0 = soby(X), gy1 = soby(Y), gy2 = soby(Z);
+  double n0 = __dsub_rn(__dmul_rn(gx1, gy2), __dmul_rn(gx2, gy1));
+  double n1 = __dsub_rn(__dmul_rn(gx2, gy0), __dmul_rn(gx0, gy2));
+  double n2 = __dsub_rn(__dmul_rn(gx0, gy1), __dmul_rn(gx1, gy0));
+  const double nn = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2)));
+  const double den = fmax(nn, 1e-12);
+  n0 = __ddiv_rn(n0, den); n1 = __ddiv_rn(n1, den); n2 = __ddiv_rn(n2, den);
+  // depth2xyz (src/utils/geometry.py:150-171): (u-cx)/fx in float32, then float64 * depth
+  const double xc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)u, cam.cx), cam.fx), zc);
+  const double yc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)v, cam.cy), cam.fy), zc);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double t0 = (double)cam.T[r * 4 + 0], t1 = (double)cam.T[r * 4 + 1], t2 = (double)cam.T[r * 4 + 2],
+                 t3 = (double)cam.T[r * 4 + 3];
+    const double p = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xc, t0), __dmul_rn(yc, t1)), __dmul_rn(zc, t2)), t3);
+    const double q = __dadd_rn(__dadd_rn(__dmul_rn(n0, t0), __dmul_rn(n1, t1)), __dmul_rn(n2, t2));
+    out[r] = (float)p;
+    out[3 + r] = (float)q;
+  }
+  return true;
+}
+
+struct EncSrc {
+  const uint16_t* depth;   // FROM_DEPTH
+  Camera cam;
+  const float* pts6;       // !FROM_DEPTH
+  int64_t n_points;
+};
+
+__device__ __forceinline__ void scatter_row(const MapDev& m, int32_t flat, int32_t row, const float (&y)[8]) {
+  const int32_t old = atomicCAS(&m.ftable[flat], kEmpty, row);
+  const int32_t slot = old == kEmpty ? row : old;
+  if (old == kEmpty) {
+    m.fkeys[row] = flat;
+    const int32_t pos = atomicAdd(&m.ctr[1], 1);
+    m.touched[pos] = row;
+  }
+  atomicAdd(&m.fcnt[slot], 1);
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(m.fsum + (size_t)slot * kFeat);
+#pragma unroll
+  for (int j = 0; j < kFeat; ++j) {
+    const long long q = __double2ll_rn((double)y[j] * kFixScale);
+    atomicAdd(s + j, (unsigned long long)q);
+  }
+}
+
+}  // namespace bnv

@@ -1,0 +1,318 @@
+// tcgen05 / TMEM / mbarrier building blocks for the tensor-core MLP chain (sm_100a only).
+//
+// The tiny tcnn-style MLPs (n_in -> 64 -> 64 -> 64 -> n_out, ReLU, no bias) are evaluated for
+// 128-row tiles as four chained UMMAs whose A operand never leaves tensor memory:
+//
+//   registers --tcgen05.st--> TMEM A (fp16 [128 x K]) --tcgen05.mma (B = weights in smem)--> TMEM D
+//   (fp32 [128 x 64]) --tcgen05.ld--> registers (ReLU + cvt.f16x2) --tcgen05.st--> TMEM A  ...
+//
+// Row r of a tile is TMEM lane r and is owned by thread r of a 128-thread "row warpgroup", so the
+// activations need no shared-memory round trip and no swizzled layouts; only the weights (B, K-major,
+// no swizzle) sit in shared memory, loaded once per persistent CTA.  Thread 0 of each row warpgroup
+// issues that warpgroup's UMMAs; several warpgroups (one TMEM slot each) keep the tensor pipe busy
+// while the others run their epilogues.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "bnv_common.cuh"
+
+namespace bnv {
+namespace tc {
+
+constexpr int kRowsPerTile = 128;
+constexpr int kSlotCols = 128;       // TMEM columns per in-flight tile: D [0,64) fp32, A [64,96) packed fp16
+constexpr int kACol = 64;
+
+// ---- shared-memory weight image (built on the host, bnv_tc.cu) ---------------------------------
+// Per layer: B [N x K] fp16, K-major, SWIZZLE_NONE canonical layout:
+//   byte(n, k) = (k / 8) * LBO + (n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2,   LBO = (N / 8) * 128
+// i.e. 8x8 core matrices of 128 contiguous bytes; SBO (between 8-row groups) = 128 B.
+struct WeightImage {
+  int k[4];          // K of each layer (in_pad, 64, 64, 64)
+  int n[4];          // N of each layer (64, 64, 64, 16)
+  int off[4];        // byte offset of each layer's block
+  int bytes;
+};
+
+__host__ __device__ inline WeightImage weight_image(int in_pad) {
+  WeightImage w{};
+  const int ks[4] = {in_pad, 64, 64, 64};
+  const int ns[4] = {64, 64, 64, 16};
+  int o = 0;
+  for (int l = 0; l < 4; ++l) {
+    w.k[l] = ks[l];
+    w.n[l] = ns[l];
+    w.off[l] = o;
+    o += ks[l] * ns[l] * 2;
+  }
+  w.bytes = o;
+  return w;
+}
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]; issued by ONE thread
+__device__ __forceinline__ void umma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all tcgen05 ops issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// instruction descriptor: f16 x f16 -> f32, both K-major, M = 128 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t idesc_f16_m128(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// ---- TMEM <-> registers: 32 lanes x 32-bit, thread i of the warp <-> lane (32 * (warp % 4) + i) --
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// two fp32 -> packed fp16x2 (lo = a, hi = b), optionally with ReLU, one instruction
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t lo_bits, uint32_t hi_bits) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi_bits)), "f"(__uint_as_float(lo_bits)));
+  return r;
+}
+
+// ---- per-thread view of one TMEM slot ------------------------------------------------------------------
+// Each 128-thread row warpgroup owns one TMEM slot and one mbarrier.  After the warpgroup has stored
+// the A operand of the next layer (tcgen05.st + wait + named barrier), its thread 0 issues that
+// layer's UMMAs itself and commits them to the warpgroup's mbarrier; the tensor pipe interleaves the
+// UMMAs of the different warpgroups, so no dedicated MMA warp (and no polling) is needed.
+struct RowChain {
+  uint32_t t_d;        // TMEM address of this warp's lanes, column 0 of the slot (D)
+  uint32_t t_a;        // ... column kACol of the slot (A)
+  uint32_t d_slot;     // slot base (lane 0), for the issuing thread
+  uint64_t* bar_d;     // "D of the last issued layer is complete" (tcgen05.commit, count 1)
+  uint32_t par_d;      // phase parity of bar_d this thread waits for next
+  uint32_t w_saddr;    // shared-memory address of the weight image
+  int bar_id;          // named barrier of this warpgroup (1 + warpgroup index)
+  bool issuer;         // thread 0 of the warpgroup
+};
+
+__device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
+
+// All rows of the tile have their A operand in TMEM -> run layer L (compile-time K, N) on the tensor core
+template <int K, int N>
+__device__ __forceinline__ void chain_issue_layer(RowChain& c, int w_off) {
+  tmem_wait_st();
+  tc_fence_before();
+  wg_sync(c.bar_id);
+  if (c.issuer) {
+    tc_fence_after();
+    constexpr uint32_t lbo = (uint32_t)(N / 8) * 128u;
+    constexpr uint32_t idesc = idesc_f16_m128(N);
+    const uint32_t b0 = c.w_saddr + w_off;
+#pragma unroll
+    for (int kk = 0; kk < K / 16; ++kk)
+      umma_ts_f16(c.d_slot, c.d_slot + kACol + kk * 8, smem_desc_kmajor(b0 + kk * 2 * lbo, lbo, 128), idesc,
+                  kk > 0 ? 1u : 0u);
+    umma_commit(c.bar_d);
+  }
+}
+__device__ __forceinline__ void chain_wait_d(RowChain& c) {
+  mbar_wait(c.bar_d, c.par_d);
+  c.par_d ^= 1;
+  tc_fence_after();
+}
+
+// hidden layer epilogue: D (64 fp32 columns of this row) -> ReLU -> fp16 -> A (32 packed columns)
+__device__ __forceinline__ void chain_hidden_epilogue(RowChain& c) {
+  uint32_t v[32], w[32];
+  tmem_ld32(c.t_d, v);
+  tmem_ld32(c.t_d + 32, w);
+  tmem_wait_ld();
+  uint32_t a[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
+    a[16 + i] = pack_relu_f16x2(w[2 * i], w[2 * i + 1]);
+  }
+  tmem_st32(c.t_a, a);
+}
+
+// Run one 128-row tile through the 4-layer MLP.  `in` = this thread's input row as INW packed fp16x2
+// words (ones-padded to in_pad = 2 * INW).  On return `out` holds the first NOUT outputs of the row.
+// Must be called by all 128 threads of the warpgroup.
+template <int INW, int NOUT>
+__device__ __forceinline__ void chain_run(RowChain& c, const uint32_t (&in)[INW], float (&out)[NOUT]) {
+  static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
+  static_assert(NOUT == 8 || NOUT == 1, "n_out must be 8 or 1");
+  constexpr int KIN = 2 * INW;
+  constexpr int off1 = KIN * 64 * 2, off2 = off1 + 64 * 64 * 2, off3 = off2 + 64 * 64 * 2;
+  if constexpr (INW == 8) tmem_st8(c.t_a, in); else tmem_st16(c.t_a, in);
+  chain_issue_layer<KIN, 64>(c, 0);
+  chain_wait_d(c);
+  chain_hidden_epilogue(c);
+  chain_issue_layer<64, 64>(c, off1);
+  chain_wait_d(c);
+  chain_hidden_epilogue(c);
+  chain_issue_layer<64, 64>(c, off2);
+  chain_wait_d(c);
+  chain_hidden_epilogue(c);
+  chain_issue_layer<64, 16>(c, off3);
+  chain_wait_d(c);
+  if constexpr (NOUT == 8) {
+    uint32_t r[8];
+    tmem_ld8(c.t_d, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = __uint_as_float(r[j]);
+  } else {
+    uint32_t r;
+    tmem_ld1(c.t_d, r);
+    tmem_wait_ld();
+    out[0] = __uint_as_float(r);
+  }
+}
+
+// CTA-level setup shared by the tensor-core kernels: NWG row warpgroups, one TMEM slot + mbarrier each
+template <int NWG>
+struct TcShared {
+  uint64_t bar_d[NWG];
+  uint32_t tmem_base;
+};
+
+template <int NWG>
+__device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
+                                             int w_bytes) {
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
+  // weights: global -> shared (image is already in the UMMA canonical layout), 16 B per thread step
+  for (int i = tid * 16; i < w_bytes; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(s_weights + i) = __ldg(reinterpret_cast<const uint4*>(g_weights + i));
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < NWG; ++g) mbar_init(&sh.bar_d[g], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&sh.tmem_base, NWG * kSlotCols);
+  // make the generic-proxy weight stores visible to the tensor core's async-proxy reads
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  RowChain c;
+  const uint32_t base = sh.tmem_base;
+  c.d_slot = base + wg * kSlotCols;
+  c.t_d = c.d_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  c.t_a = c.t_d + kACol;
+  c.bar_d = &sh.bar_d[wg];
+  c.par_d = 0;
+  c.w_saddr = smem_u32(s_weights);
+  c.bar_id = 1 + wg;
+  c.issuer = (tid & 127) == 0;
+  return c;
+}
+
+template <int NWG>
+__device__ __forceinline__ void tc_teardown(TcShared<NWG>& sh) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem_base, NWG * kSlotCols);
+}
+
+}  // namespace tc
+}  // namespace bnv

@@ -1,0 +1,118 @@
+"""GPU (B200): the tcgen05 tensor-core mode (BNV_MLP_TC16: fp16 operands, fp32 accumulation in TMEM).
+
+Bars: voxel ids / keys / counts bit-exact (index maths never touches the tensor cores); SDF within the
+1e-4 abs budget of BASELINE.json against the fp32 goldens; MLP outputs additionally within fp16
+operand-rounding noise of the fp16-emulating oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bnv_oracle as O
+from bnv_fusion_b200 import config, synth
+from test_gpu_parity import _depth_to_dev, _golden_map_sorted, _map_sorted, _volume, dev, model  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+SDF_ATOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def tc_mode():
+    config.set_mlp_mode("tc16")
+    yield
+    config.set_mlp_mode("fp32")
+
+
+def _close_fp16(a, ref, rel=4e-3, abs_=4e-3):
+    err = np.abs(a - ref)
+    assert (err <= abs_ + rel * np.abs(ref)).all(), (err.max(), np.abs(ref).max())
+
+
+def test_tc_mlp_forward(model, golden_dir, tcnn_params, dev):
+    g = np.load(os.path.join(golden_dir, "golden_edge.npz"))
+    rng = np.random.default_rng(0)
+    for n in (64, 1, 127, 128, 129, 5000, 200_000):
+        xe = rng.uniform(-1, 1, size=(n, 6)).astype(np.float32)
+        ye = model.pointnet_backbone.model(torch.from_numpy(xe).to(dev)).cpu().numpy()
+        ref16 = O.mlp_forward(tcnn_params["encoder"], xe, 6, 8, mode="fp16")
+        _close_fp16(ye, ref16, rel=2e-3, abs_=2e-3)
+        xd = np.concatenate([rng.uniform(-1, 1, size=(n, 9)), rng.normal(0, 0.8, size=(n, 8))], 1).astype(np.float32)
+        yd = model.nerf.model(torch.from_numpy(xd).to(dev)).cpu().numpy()
+        ref16 = O.mlp_forward(tcnn_params["decoder"], xd, 17, 1, mode="fp16")
+        _close_fp16(yd, ref16, rel=2e-3, abs_=2e-3)
+        ref32 = O.mlp_forward(tcnn_params["decoder"], xd, 17, 1, mode="fp32")
+        assert np.abs(yd - ref32).max() * 0.01 < SDF_ATOL          # SDF = y * voxel_size
+    ye = model.pointnet_backbone.model(torch.from_numpy(g["kat_enc_x"]).to(dev)).cpu().numpy()
+    _close_fp16(ye, g["kat_enc_y"])
+
+
+@pytest.mark.parametrize("path", ["api", "fused_depth"])
+def test_tc_parity64_stream(model, golden_dir, dev, path):
+    g = np.load(os.path.join(golden_dir, "golden_parity64.npz"))
+    spec = synth.stream_spec("parity64")
+    vol = _volume(spec, dev, pool_capacity=1 << 16)
+    for fi in range(g["depth"].shape[0]):
+        d, K, T = g["depth"][fi], g["K"][fi], g["T_wc"][fi]
+        if path == "fused_depth":
+            model.fuse_depth_frame(vol, _depth_to_dev(d, dev), K, T, spec.max_depth)
+            continue
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        pts6 = torch.from_numpy(O.backproject(depth, mask, K, T)).to(dev)
+        feats, counts, flat, coords, navg = model.encode_pointcloud(
+            pts6[None], vol.n_xyz, vol.min_coords, vol.max_coords, vol.voxel_size, return_dense=False)
+        if f"recip/f{fi}_flat" in g.files:
+            assert np.array_equal(flat.cpu().numpy(), g[f"recip/f{fi}_flat"])
+            assert np.array_equal(counts.cpu().numpy(), g[f"recip/f{fi}_counts"])
+            _close_fp16(feats.cpu().numpy(), g[f"recip/f{fi}_feats"])
+        model._integrate(vol, coords, feats, counts)
+    vol.check_status()
+    flat, feats, w, h = _map_sorted(vol)
+    rflat, rfeats, rw, rh = _golden_map_sorted(g, "recip", vol._n_xyz_host)
+    assert np.array_equal(flat, rflat)                      # bit-exact voxel set
+    np.testing.assert_allclose(w, rw, atol=1e-6, rtol=0)    # weights depend on counts only
+    _close_fp16(feats, rfeats)
+    prior = torch.from_numpy(g["recip/tsdf_delta"]).to(dev)[None, None]
+    qm = torch.from_numpy(g["recip/q_mesh"]).to(dev)[None]
+    for p, key in ((None, "sdf_mesh"), (prior, "sdf_mesh_prior")):
+        sdf = vol.decode_pts(qm, model.nerf, p, is_coords=True)[0, :, :, 0].cpu().numpy()
+        assert np.abs(sdf - g["recip/" + key]).max() <= SDF_ATOL, np.abs(sdf - g["recip/" + key]).max()
+    qr = torch.from_numpy(g["recip/q_rand"]).to(dev)[None, :, None, :]
+    sdf = vol.decode_pts(qr, model.nerf, prior, is_coords=True)[0, :, 0, 0].cpu().numpy()
+    assert np.abs(sdf - g["recip/sdf_rand_prior"]).max() <= SDF_ATOL
+
+
+def test_tc_full_frame_paths_agree(model, dev):
+    from bnv_fusion_b200.model import backproject
+    spec = synth.stream_spec("lounge")
+    vols = [_volume(spec, dev, pool_capacity=1 << 21) for _ in range(2)]
+    for fi in range(2):
+        d, K, T = synth.make_frame(spec, fi, seed=1)
+        dd = _depth_to_dev(d, dev)
+        model.fuse_depth_frame(vols[0], dd, K, T, spec.max_depth)
+        pts = backproject(vols[1], dd, K, T, spec.max_depth)
+        feats, counts, flat, coords, navg = model.encode_pointcloud(
+            pts[None], vols[1].n_xyz, vols[1].min_coords, vols[1].max_coords, vols[1].voxel_size, return_dense=False)
+        model._integrate(vols[1], coords, feats, counts)
+    a, b = _map_sorted(vols[0]), _map_sorted(vols[1])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # fp32 CUDA-core mode on the same frames: same voxels, features within fp16 noise
+    config.set_mlp_mode("fp32")
+    v32 = _volume(spec, dev, pool_capacity=1 << 21)
+    for fi in range(2):
+        d, K, T = synth.make_frame(spec, fi, seed=1)
+        model.fuse_depth_frame(v32, _depth_to_dev(d, dev), K, T, spec.max_depth)
+    c = _map_sorted(v32)
+    config.set_mlp_mode("tc16")
+    assert np.array_equal(a[0], c[0]) and np.array_equal(a[2], c[2])
+    _close_fp16(a[1], c[1])
+    # decode on the 512^3 map: tensor-core vs CUDA-core SDF within budget
+    vol = vols[0]
+    coords, _, _, _ = vol.to_tensor()
+    vol.weights += 8.0
+    tc = vol.decode_voxel_blocks(model.nerf)
+    config.set_mlp_mode("fp32")
+    ref = vol.decode_voxel_blocks(model.nerf)
+    config.set_mlp_mode("tc16")
+    assert float((tc - ref).abs().max()) <= SDF_ATOL
