@@ -7,7 +7,7 @@ DEFAULT_POOL_CAPACITY = 1 << 24     # voxel value-pool rows per map (0.67 GB of 
 DEFAULT_MAX_POINTS = 640 * 480      # most points one frame may carry (sizes per-frame scratch)
 
 _MODE = {"fp32": _lib.MLP_FP32, "tc16": _lib.MLP_TC16}
-_mode = _MODE[os.environ.get("BNV_MLP_MODE", "fp32").lower()]
+_mode = _MODE[os.environ.get("BNV_MLP_MODE", "tc16").lower()]
 
 
 def set_mlp_mode(name: str):

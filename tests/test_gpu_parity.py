@@ -19,6 +19,15 @@ SDF_ATOL = 1e-4          # the contract
 SDF_ATOL_FP32 = 2e-6     # what the fp32 path actually achieves
 
 
+@pytest.fixture(autouse=True)
+def fp32_mode():
+    """This file pins the exact-parity CUDA-core arithmetic; test_gpu_tc.py covers the tensor cores."""
+    from bnv_fusion_b200 import config
+    config.set_mlp_mode("fp32")
+    yield
+    config.set_mlp_mode("tc16")
+
+
 @pytest.fixture(scope="module")
 def dev():
     assert torch.cuda.is_available(), "gpu tests need a CUDA device"

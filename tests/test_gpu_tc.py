@@ -22,7 +22,6 @@ SDF_ATOL = 1e-4
 def tc_mode():
     config.set_mlp_mode("tc16")
     yield
-    config.set_mlp_mode("fp32")
 
 
 def _close_fp16(a, ref, rel=4e-3, abs_=4e-3):
