@@ -6,6 +6,8 @@
 // (src/models/fusion/modules.py:81-123), tcnnNeRFModel.geo_forward (modules.py:249-253),
 // F.grid_sample(nearest) of the prior (sparse_volume.py:819-832), meshlize sampling (:717-731).
 // This file holds the fp32 CUDA-core variant (BNV_MLP_FP32); the tcgen05 variant is in bnv_tc.cu.
+#include <stdlib.h>
+
 #include "bnv_common.cuh"
 #include "bnv_decode_common.cuh"
 #include "bnv_mlp_simt.cuh"
@@ -82,6 +84,7 @@ static int decode_common(bnv_map_t* map, DecArgs& a, const bnv_mlp_t* dec, int m
     return BNV_E_ARG;
   }
   a.tsdf = tsdf;
+  { const char* e = getenv("BNV_DEBUG_DECODE"); a.debug = e ? atoi(e) : 0; }
   if (tsdf) {
     if (!tsdf_dims || tsdf_dims[0] <= 0 || tsdf_dims[1] <= 0 || tsdf_dims[2] <= 0) { set_error("decode: bad tsdf dims"); return BNV_E_ARG; }
     for (int i = 0; i < 3; ++i) {

@@ -88,6 +88,25 @@ struct EncSrc {
   int64_t n_points;
 };
 
+// split form of scatter_row: claim the voxel's scratch row first (the CAS round trip can then overlap
+// other work), add the encoded features later (fire-and-forget reductions)
+__device__ __forceinline__ int32_t claim_row(const MapDev& m, int32_t flat, int32_t row) {
+  const int32_t old = atomicCAS(&m.ftable[flat], kEmpty, row);
+  if (old == kEmpty) {
+    m.fkeys[row] = flat;
+    const int32_t pos = atomicAdd(&m.ctr[1], 1);
+    m.touched[pos] = row;
+    return row;
+  }
+  return old;
+}
+__device__ __forceinline__ void add_row(const MapDev& m, int32_t slot, const float (&y)[8]) {
+  atomicAdd(&m.fcnt[slot], 1);
+  unsigned long long* s = reinterpret_cast<unsigned long long*>(m.fsum + (size_t)slot * kFeat);
+#pragma unroll
+  for (int j = 0; j < kFeat; ++j) atomicAdd(s + j, (unsigned long long)__double2ll_rn((double)y[j] * kFixScale));
+}
+
 __device__ __forceinline__ void scatter_row(const MapDev& m, int32_t flat, int32_t row, const float (&y)[8]) {
   const int32_t old = atomicCAS(&m.ftable[flat], kEmpty, row);
   const int32_t slot = old == kEmpty ? row : old;

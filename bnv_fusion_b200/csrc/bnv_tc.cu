@@ -3,6 +3,7 @@
 // decoder MLP -> trilinear blend + prior).  fp16 operands, fp32 accumulation in tensor memory.
 // Building blocks and the data flow are described in bnv_tc.cuh.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -106,19 +107,31 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     }
     const uint32_t nrm12 = pack_f16x2(inb ? p[4] : 0.f, inb ? p[5] : 0.f);
     const float nrm0 = inb ? p[3] : 0.f;
+    // phase A: claim the 8 corner voxels' scratch rows (8 independent CAS round trips in flight)
+    int32_t slot[8];
     int n_rows = 0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
       float nb[3];
       corner_of(k, fl, ce, nb);
       const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-      const bool mine = inb && owns(g, ix);
-      if (g.world > 1) {                       // warpgroup-uniform skip of corners nobody owns
+      slot[k] = -1;
+      if (inb && owns(g, ix)) {
+        slot[k] = claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
+        ++n_rows;
+      }
+    }
+    // phase B: encoder MLP per corner row on the tensor core, accumulate into the claimed rows
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float nb[3];
+      corner_of(k, fl, ce, nb);
+      if (g.world > 1) {                       // warpgroup-uniform skip of corners nobody here owns
         int any;
         asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.cta.red.or.pred q, %2, 128, p;\n\t"
                      "selp.u32 %0, 1, 0, q;\n\t}"
                      : "=r"(any)
-                     : "r"((int)mine), "r"(c.bar_id)
+                     : "r"((int)(slot[k] >= 0)), "r"(c.bar_id)
                      : "memory");
         if (!any) continue;
       }
@@ -132,11 +145,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       const uint32_t in[8] = {pack_f16x2(xr[0], xr[1]), pack_f16x2(xr[2], nrm0), nrm12, kOnes, kOnes, kOnes, kOnes, kOnes};
       float y[8];
       chain_run<8, 8>(c, in, y);
-      if (mine) {
-        const int32_t flat = ix * g.nyz + iy * g.n[2] + iz;                              // rule A5
-        scatter_row(m, flat, (int32_t)(idx * 8 + k), y);
-        ++n_rows;
-      }
+      if (slot[k] >= 0) add_row(m, slot[k], y);
     }
     const unsigned mv = __ballot_sync(0xffffffffu, valid);
     const unsigned mi = __ballot_sync(0xffffffffu, inb);
@@ -153,11 +162,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
 }
 
 // ---- fused decode -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint8_t* __restrict__ gW,
-                                                                int w_bytes) {
+template <int NWG>
+__global__ void __launch_bounds__(NWG * 128, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint8_t* __restrict__ gW,
+                                                                 int w_bytes) {
+  constexpr int kNWG = NWG;
   extern __shared__ __align__(128) uint8_t smem[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem);
-  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<4>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
   for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     {
       float nb[3];
       corner_of(0, fl, ce, nb);
-      if (live) gather_corner(m, a, nb, feat, wt);
+      if (live && a.debug != 2) gather_corner(m, a, nb, feat, wt);
       else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) feat[j] = 0.f;
@@ -211,9 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
       if (k < 7) {                                                                       // prefetch next corner
         float nb2[3];
         corner_of(k + 1, fl, ce, nb2);
-        if (live) gather_corner(m, a, nb2, feat, wt);
+        if (live && a.debug != 2) gather_corner(m, a, nb2, feat, wt);
       }
       float y[1];
+      if (a.debug == 1) y[0] = __uint_as_float(in[0] ^ in[5] ^ in[8]); else
       chain_run<16, 1>(c, in, y);                                                        // D7
       const float wn = __fdiv_rn(corner_weight(cq, nb), wsum);                           // D2
       sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], m.g.vs), wn));                      // D4, D5
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
       if (a.out_mask) a.out_mask[q] = mask ? 1 : 0;
     }
   }
-  tc_teardown<kNWG>(S.sh);
+  tc_teardown<4>(S.sh);
 }
 
 }  // namespace tc
@@ -236,6 +248,8 @@ int bnv_internal_pack_tc_weights(bnv_mlp_t* mlp, const float* params) {
   const WeightImage wi = weight_image(mlp->in_pad);
   std::vector<__half> img((size_t)wi.bytes / 2);
   const float* W = params;
+  memcpy(reinterpret_cast<uint8_t*>(img.data()) + wi.off_w3f32,
+         params + (size_t)64 * mlp->in_pad + 2 * 64 * 64, 64 * sizeof(float));   // W3 row 0
   for (int l = 0; l < 4; ++l) {
     const int K = wi.k[l], N = wi.n[l];
     const int lbo = (N / 8) * 128;
@@ -298,10 +312,20 @@ int bnv_internal_encode_tc(bnv_map_t* map, const void* srcp, int from_depth, int
 
 int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
   const size_t smem = tc_smem_bytes(dec->in_pad);
-  int rc = set_smem(decode_tc_kernel, smem);
-  if (rc) return rc;
+  const char* e = getenv("BNV_TC_NWG");
+  const int nwg = e ? atoi(e) : 4;
   const int grid = tc_grid((a.n_queries + 127) / 128);
-  decode_tc_kernel<<<grid, kThreads, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+  int rc;
+  if (nwg == 2) {
+    rc = set_smem(decode_tc_kernel<2>, smem); if (rc) return rc;
+    decode_tc_kernel<2><<<grid, 256, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+  } else if (nwg == 3) {
+    rc = set_smem(decode_tc_kernel<3>, smem); if (rc) return rc;
+    decode_tc_kernel<3><<<grid, 384, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+  } else {
+    rc = set_smem(decode_tc_kernel<4>, smem); if (rc) return rc;
+    decode_tc_kernel<4><<<grid, 512, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+  }
   BNV_LAUNCH_CHECK("decode_tc_kernel");
   return BNV_OK;
 }

@@ -31,6 +31,8 @@ struct WeightImage {
   int k[4];          // K of each layer (in_pad, 64, 64, 64)
   int n[4];          // N of each layer (64, 64, 64, 16)
   int off[4];        // byte offset of each layer's block
+  int off_w3f32;     // byte offset of the fp32 copy of W3 row 0 (64 floats): single-output layers run on
+                     // the CUDA cores straight from the fp32 accumulators (no fp16 rounding of h3)
   int bytes;
 };
 
@@ -45,6 +47,8 @@ __host__ __device__ inline WeightImage weight_image(int in_pad) {
     w.off[l] = o;
     o += ks[l] * ns[l] * 2;
   }
+  w.off_w3f32 = o;
+  o += 64 * 4;
   w.bytes = o;
   return w;
 }
@@ -189,8 +193,9 @@ struct RowChain {
   uint64_t* bar_d;     // "D of the last issued layer is complete" (tcgen05.commit, count 1)
   uint32_t par_d;      // phase parity of bar_d this thread waits for next
   uint32_t w_saddr;    // shared-memory address of the weight image
+  const uint8_t* w_gen; // same, generic pointer (fp32 W3 for the CUDA-core output layer)
   int bar_id;          // named barrier of this warpgroup (1 + warpgroup index)
-  bool issuer;         // thread 0 of the warpgroup
+  bool issuer;         // the warpgroup's UMMA-issuing thread (lane 0 of warp wg % 4)
 };
 
 __device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
@@ -234,17 +239,28 @@ __device__ __forceinline__ void chain_hidden_epilogue(RowChain& c) {
   tmem_st32(c.t_a, a);
 }
 
+struct NoShadow {
+  __device__ __forceinline__ void operator()() const {}
+};
+
 // Run one 128-row tile through the 4-layer MLP.  `in` = this thread's input row as INW packed fp16x2
 // words (ones-padded to in_pad = 2 * INW).  On return `out` holds the first NOUT outputs of the row.
-// Must be called by all 128 threads of the warpgroup.
-template <int INW, int NOUT>
-__device__ __forceinline__ void chain_run(RowChain& c, const uint32_t (&in)[INW], float (&out)[NOUT]) {
+// Must be called by all 128 threads of the warpgroup.  `shadow()` is invoked once right after the
+// first layer has been issued: work placed there (preparing the next row) runs in the shadow of the
+// MMA round trip (~500 cycles of issue + commit + wake latency, tools/umma_bench.cu).
+//   NOUT == 8 (encoder): all four layers on the tensor core (output layer N = 16).
+//   NOUT == 1 (decoder): the 64 -> 1 output layer is 64 FMAs per row on the CUDA cores, taken from the
+//   fp32 accumulators of layer 2 -- a whole MMA round trip for 0.7 % of the FLOPs is not worth it.
+template <int INW, int NOUT, class Shadow = NoShadow>
+__device__ __forceinline__ void chain_run(RowChain& c, const uint32_t (&in)[INW], float (&out)[NOUT],
+                                          Shadow shadow = Shadow()) {
   static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
   static_assert(NOUT == 8 || NOUT == 1, "n_out must be 8 or 1");
   constexpr int KIN = 2 * INW;
   constexpr int off1 = KIN * 64 * 2, off2 = off1 + 64 * 64 * 2, off3 = off2 + 64 * 64 * 2;
   if constexpr (INW == 8) tmem_st8(c.t_a, in); else tmem_st16(c.t_a, in);
   chain_issue_layer<KIN, 64>(c, 0);
+  shadow();
   chain_wait_d(c);
   chain_hidden_epilogue(c);
   chain_issue_layer<64, 64>(c, off1);
@@ -252,20 +268,36 @@ __device__ __forceinline__ void chain_run(RowChain& c, const uint32_t (&in)[INW]
   chain_hidden_epilogue(c);
   chain_issue_layer<64, 64>(c, off2);
   chain_wait_d(c);
-  chain_hidden_epilogue(c);
-  chain_issue_layer<64, 16>(c, off3);
-  chain_wait_d(c);
   if constexpr (NOUT == 8) {
+    chain_hidden_epilogue(c);
+    chain_issue_layer<64, 16>(c, off3);
+    chain_wait_d(c);
     uint32_t r[8];
     tmem_ld8(c.t_d, r);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 8; ++j) out[j] = __uint_as_float(r[j]);
   } else {
-    uint32_t r;
-    tmem_ld1(c.t_d, r);
+    constexpr int off_w3 = off3 + 16 * 64 * 2;
+    uint32_t v[32], w[32];
+    tmem_ld32(c.t_d, v);
+    tmem_ld32(c.t_d + 32, w);
     tmem_wait_ld();
-    out[0] = __uint_as_float(r);
+    const float4* w3 = reinterpret_cast<const float4*>(c.w_gen + off_w3);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 wa = w3[i], wb = w3[8 + i];
+      acc0 = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), wa.x, acc0);
+      acc1 = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), wa.y, acc1);
+      acc2 = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), wa.z, acc2);
+      acc3 = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), wa.w, acc3);
+      acc0 = fmaf(fmaxf(__uint_as_float(w[4 * i + 0]), 0.f), wb.x, acc0);
+      acc1 = fmaf(fmaxf(__uint_as_float(w[4 * i + 1]), 0.f), wb.y, acc1);
+      acc2 = fmaf(fmaxf(__uint_as_float(w[4 * i + 2]), 0.f), wb.z, acc2);
+      acc3 = fmaf(fmaxf(__uint_as_float(w[4 * i + 3]), 0.f), wb.w, acc3);
+    }
+    out[0] = (acc0 + acc1) + (acc2 + acc3);
   }
 }
 
@@ -302,8 +334,10 @@ __device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weigh
   c.bar_d = &sh.bar_d[wg];
   c.par_d = 0;
   c.w_saddr = smem_u32(s_weights);
+  c.w_gen = s_weights;
   c.bar_id = 1 + wg;
-  c.issuer = (tid & 127) == 0;
+  // issuing threads sit in different SM sub-partitions (warp % 4): the UMMA issue rate is per sub-partition
+  c.issuer = (tid & 127) == 32 * (wg & 3);
   return c;
 }
 
