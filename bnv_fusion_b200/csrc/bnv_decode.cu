@@ -84,7 +84,6 @@ static int decode_common(bnv_map_t* map, DecArgs& a, const bnv_mlp_t* dec, int m
     return BNV_E_ARG;
   }
   a.tsdf = tsdf;
-  { const char* e = getenv("BNV_DEBUG_DECODE"); a.debug = e ? atoi(e) : 0; }
   if (tsdf) {
     if (!tsdf_dims || tsdf_dims[0] <= 0 || tsdf_dims[1] <= 0 || tsdf_dims[2] <= 0) { set_error("decode: bad tsdf dims"); return BNV_E_ARG; }
     for (int i = 0; i < 3; ++i) {

@@ -20,7 +20,6 @@ struct DecArgs {
   float tm1[3];               // (float)(T - 1)
   float* out_sdf;
   uint8_t* out_mask;
-  int debug;                  // profiling experiments only (BNV_DEBUG_DECODE): 1 = no MMA chain, 2 = no gather
 };
 
 // corner order of fusion/utils.get_neighbors (src/models/fusion/utils.py:98-167):

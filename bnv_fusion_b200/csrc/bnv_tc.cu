@@ -3,6 +3,7 @@
 // decoder MLP -> trilinear blend + prior).  fp16 operands, fp32 accumulation in tensor memory.
 // Building blocks and the data flow are described in bnv_tc.cuh.
 #include <cuda_fp16.h>
+#include <limits.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -52,10 +53,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
     const int64_t i = tile * 128 + r;
     float xi[2 * INW];
 #pragma unroll
-    for (int k = 0; k < 2 * INW; ++k) xi[k] = 1.0f;
-    if (i < n) {
-#pragma unroll
-      for (int k = 0; k < NIN; ++k) xi[k] = __ldg(x + i * NIN + k);
+    for (int k = 0; k < 2 * INW; ++k) {
+      const int src = NIN == 17 ? dec_perm(k) : enc_perm(k);     // column order of the packed W0
+      xi[k] = (src < NIN && i < n) ? __ldg(x + i * NIN + src) : 1.0f;
     }
     uint32_t in[INW];
 #pragma unroll
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       fl[a] = floorf(cc[a]);
       ce[a] = ceilf(cc[a]);
     }
-    const uint32_t nrm12 = pack_f16x2(inb ? p[4] : 0.f, inb ? p[5] : 0.f);
-    const float nrm0 = inb ? p[3] : 0.f;
+    const uint32_t nrm01 = pack_f16x2(inb ? p[3] : 0.f, inb ? p[4] : 0.f);
+    const uint32_t nrm2o = pack_f16x2(inb ? p[5] : 0.f, 1.f);
     // phase A: claim the 8 corner voxels' scratch rows (8 independent CAS round trips in flight)
     int32_t slot[8];
     int n_rows = 0;
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
         const float rel = __fmul_rn(__fsub_rn(cc[a], nb[a]), g.vs);                     // rule A4
         xr[a] = __fmul_rn(rel, g.inv_vs);
       }
-      // row = [x0 x1 x2 n0 n1 n2 | 1 x 10]  (tcnn pads the 6 inputs to 16 with ones)
-      const uint32_t in[8] = {pack_f16x2(xr[0], xr[1]), pack_f16x2(xr[2], nrm0), nrm12, kOnes, kOnes, kOnes, kOnes, kOnes};
+      // row = [x 1 | y 1 | z 1 | n0 n1 | n2 1 | 1 x 6]  (enc_perm: tcnn pads the 6 inputs to 16 with ones)
+      const uint32_t in[8] = {pack_f16x2(xr[0], 1.f), pack_f16x2(xr[1], 1.f), pack_f16x2(xr[2], 1.f), nrm01, nrm2o, kOnes, kOnes, kOnes};
       float y[8];
       chain_run<8, 8>(c, in, y);
       if (slot[k] >= 0) add_row(m, slot[k], y);
@@ -162,78 +162,123 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
 }
 
 // ---- fused decode -----------------------------------------------------------------------------------
+// exported rows -> packed fp16 features (16 B per row) for the gather
+__global__ void pack_rows_kernel(const float* __restrict__ feats, int64_t n, uint4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = reinterpret_cast<const float4*>(feats)[2 * i], b = reinterpret_cast<const float4*>(feats)[2 * i + 1];
+  out[i] = make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w));
+}
+
+struct AxisPre {       // one axis of a query, floor (s = 0) and ceil (s = 1) flavours
+  uint32_t w_ls[2];    // fp16x2 {l, sin l}
+  uint32_t w_c1[2];    // fp16x2 {cos l, 1}
+  float t[2];          // 1 - |l|
+  int32_t tab[2];      // voxel index * table stride of this axis, or INT_MIN when outside the grid
+  int32_t ts[2];       // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
+};
+
 template <int NWG>
-__global__ void __launch_bounds__(NWG * 128, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint8_t* __restrict__ gW,
-                                                                 int w_bytes) {
-  constexpr int kNWG = NWG;
+__global__ void __launch_bounds__(NWG * 128, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint4* __restrict__ packed,
+                                                                 const uint8_t* __restrict__ gW, int w_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem);
   RowChain c = tc_setup<4>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
-  for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
+  const GeomDev& g = m.g;
+  constexpr int32_t kOut = INT_MIN;
+  for (int64_t tile = (int64_t)blockIdx.x * NWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * NWG) {
     const int64_t q = tile * 128 + r;
     const bool live = q < a.n_queries;
     float cq[3] = {0.f, 0.f, 0.f};
     if (live) query_coords(m, a, q, cq);
-    float fl[3], ce[3];
+    // ---- once per query: everything that depends on one axis only ---------------------------------
+    AxisPre ax[3];
+    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
+    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
 #pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-      fl[ax] = floorf(cq[ax]);
-      ce[ax] = ceilf(cq[ax]);
-    }
-    const float wsum = corner_weight_sum(cq, fl, ce);
-    float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
-    // software pipeline: the gather of corner k+1 is in flight while corner k runs on the tensor core
-    float feat[8], wt;
-    {
-      float nb[3];
-      corner_of(0, fl, ce, nb);
-      if (live && a.debug != 2) gather_corner(m, a, nb, feat, wt);
-      else {
+    for (int d = 0; d < 3; ++d) {
+      const float nbv[2] = {floorf(cq[d]), ceilf(cq[d])};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) feat[j] = 0.f;
-        wt = 0.f;
+      for (int s = 0; s < 2; ++s) {
+        const float l = __fsub_rn(cq[d], nbv[s]);                                        // D1
+        float sn, cs;
+        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
+        ax[d].w_ls[s] = pack_f16x2(l, sn);
+        ax[d].w_c1[s] = pack_f16x2(cs, 1.0f);
+        ax[d].t[s] = __fsub_rn(1.f, fabsf(l));
+        const int iv = (int)nbv[s];
+        ax[d].tab[s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
+        ax[d].ts[s] = kOut;
+        if (a.tsdf) {                                                                    // grid_sample(nearest), D6
+          float t = __fdiv_rn(nbv[s], a.nm1[d]);
+          t = __fmul_rn(t, 2.f);
+          t = __fsub_rn(t, 1.f);
+          t = __fadd_rn(t, 1.f);
+          t = __fmul_rn(t, 0.5f);
+          t = __fmul_rn(t, a.tm1[d]);
+          const float rr = nearbyintf(t);
+          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ax[d].ts[s] = (int)rr * pstride[d];
+        }
       }
     }
-#pragma unroll 1
+    // corner k uses flavour (sx, sy, sz) = get_neighbors' order (src/models/fusion/utils.py:98-167)
+    constexpr int SX[8] = {0, 1, 0, 0, 1, 1, 0, 1}, SY[8] = {0, 0, 1, 0, 1, 0, 1, 1}, SZ[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+    float wsum = 0.f;
+#pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float nb[3];
-      corner_of(k, fl, ce, nb);
-      float l[3], sn[3], cs[3];
+      const float w = __fmul_rn(__fmul_rn(ax[0].t[SX[k]], ax[1].t[SY[k]]), ax[2].t[SZ[k]]);
+      wsum = k == 0 ? w : __fadd_rn(wsum, w);                                            // D2 normaliser
+    }
+    // ---- 8 independent table lookups in flight (_query_tensor, D3) ---------------------------------
+    int32_t slot[8];
 #pragma unroll
-      for (int ax = 0; ax < 3; ++ax) {
-        l[ax] = __fsub_rn(cq[ax], nb[ax]);                                               // D1
-        __sincosf(l[ax], &sn[ax], &cs[ax]);                                              // |l| <= 1
-      }
-      uint32_t in[16];
-      in[0] = pack_f16x2(l[0], l[1]);
-      in[1] = pack_f16x2(l[2], sn[0]);
-      in[2] = pack_f16x2(sn[1], sn[2]);
-      in[3] = pack_f16x2(cs[0], cs[1]);
-      in[4] = pack_f16x2(cs[2], feat[0]);
-      in[5] = pack_f16x2(feat[1], feat[2]);
-      in[6] = pack_f16x2(feat[3], feat[4]);
-      in[7] = pack_f16x2(feat[5], feat[6]);
-      in[8] = pack_f16x2(feat[7], 1.0f);
+    for (int k = 0; k < 8; ++k) {
+      const int32_t tx = ax[0].tab[SX[k]], ty = ax[1].tab[SY[k]], tz = ax[2].tab[SZ[k]];
+      slot[k] = kEmpty;
+      if (tx != kOut && ty != kOut && tz != kOut) slot[k] = __ldg(m.table + ((int64_t)tx + ty + tz));
+    }
+    float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
+    uint4 f_cur = make_uint4(0, 0, 0, 0), f_nxt = make_uint4(0, 0, 0, 0);
+    float w_cur = 0.f, w_nxt = 0.f;
+    if (slot[0] >= 0 && slot[0] < a.n_rows) {
+      f_cur = __ldg(packed + slot[0]);
+      w_cur = __ldg(a.weights_rows + slot[0]);
+    }
 #pragma unroll
-      for (int j = 9; j < 16; ++j) in[j] = kOnes;
-      minw = fminf(minw, wt);                                                            // D3
-      if (k < 7) {                                                                       // prefetch next corner
-        float nb2[3];
-        corner_of(k + 1, fl, ce, nb2);
-        if (live && a.debug != 2) gather_corner(m, a, nb2, feat, wt);
-      }
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t in[16] = {f_cur.x, f_cur.y, f_cur.z, f_cur.w,
+                               ax[0].w_ls[SX[k]], ax[0].w_c1[SX[k]], ax[1].w_ls[SY[k]], ax[1].w_c1[SY[k]],
+                               ax[2].w_ls[SZ[k]], ax[2].w_c1[SZ[k]], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+      minw = fminf(minw, w_cur);                                                         // D3
       float y[1];
-      if (a.debug == 1) y[0] = __uint_as_float(in[0] ^ in[5] ^ in[8]); else
-      chain_run<16, 1>(c, in, y);                                                        // D7
-      const float wn = __fdiv_rn(corner_weight(cq, nb), wsum);                           // D2
-      sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], m.g.vs), wn));                      // D4, D5
-      if (a.tsdf) dsum = __fadd_rn(dsum, __fmul_rn(tsdf_nearest(a, m.g, nb), wn));       // D6
+      chain_run<16, 1>(c, in, y, [&]() {
+        // in the shadow of the first MMA round trip: fetch the next corner's features
+        if (k < 7) {
+          f_nxt = make_uint4(0, 0, 0, 0);
+          w_nxt = 0.f;
+          const int32_t s = slot[k < 7 ? k + 1 : 7];
+          if (s >= 0 && s < a.n_rows) {
+            f_nxt = __ldg(packed + s);
+            w_nxt = __ldg(a.weights_rows + s);
+          }
+        }
+      });                                                                                // D7
+      const float wk = __fmul_rn(__fmul_rn(ax[0].t[SX[k]], ax[1].t[SY[k]]), ax[2].t[SZ[k]]);
+      const float wn = __fdiv_rn(wk, wsum);                                              // D2
+      sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                        // D4, D5
+      if (a.tsdf) {
+        const int32_t px = ax[0].ts[SX[k]], py = ax[1].ts[SY[k]], pz = ax[2].ts[SZ[k]];
+        const float dl = (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
+        dsum = __fadd_rn(dsum, __fmul_rn(dl, wn));                                       // D6
+      }
+      f_cur = f_nxt;
+      w_cur = w_nxt;
     }
     if (live) {
       bool mask;
-      a.out_sdf[q] = finish_blend(sdf, dsum, minw, a, m.g.vs, &mask);
+      a.out_sdf[q] = finish_blend(sdf, dsum, minw, a, g.vs, &mask);
       if (a.out_mask) a.out_mask[q] = mask ? 1 : 0;
     }
   }
@@ -257,7 +302,8 @@ int bnv_internal_pack_tc_weights(bnv_mlp_t* mlp, const float* params) {
     for (int n = 0; n < N; ++n)
       for (int k = 0; k < K; ++k) {
         const size_t byte = (size_t)(k / 8) * lbo + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
-        *reinterpret_cast<__half*>(base + byte) = __float2half_rn(W[(size_t)n * K + k]);   // row-major [out, in]
+        const int src = l > 0 ? k : (mlp->n_in == 17 ? dec_perm(k) : enc_perm(k));       // first layer: permuted inputs
+        *reinterpret_cast<__half*>(base + byte) = __float2half_rn(W[(size_t)n * K + src]); // row-major [out, in]
       }
     W += (size_t)N * K;
   }
@@ -312,19 +358,24 @@ int bnv_internal_encode_tc(bnv_map_t* map, const void* srcp, int from_depth, int
 
 int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
   const size_t smem = tc_smem_bytes(dec->in_pad);
-  const char* e = getenv("BNV_TC_NWG");
+  // gather-friendly copy of the exported rows: fp16x8 features, 16 B per row
+  if (a.n_rows > 0) {
+    pack_rows_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, s>>>(a.feats_rows, a.n_rows, (uint4*)map->dec_pack);
+    BNV_LAUNCH_CHECK("pack_rows_kernel");
+  }
+  const char* e = getenv("BNV_TC_NWG");      // profiling experiments only
   const int nwg = e ? atoi(e) : 4;
   const int grid = tc_grid((a.n_queries + 127) / 128);
   int rc;
   if (nwg == 2) {
     rc = set_smem(decode_tc_kernel<2>, smem); if (rc) return rc;
-    decode_tc_kernel<2><<<grid, 256, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+    decode_tc_kernel<2><<<grid, 256, smem, s>>>(map->d, a, (const uint4*)map->dec_pack, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
   } else if (nwg == 3) {
     rc = set_smem(decode_tc_kernel<3>, smem); if (rc) return rc;
-    decode_tc_kernel<3><<<grid, 384, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+    decode_tc_kernel<3><<<grid, 384, smem, s>>>(map->d, a, (const uint4*)map->dec_pack, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
   } else {
     rc = set_smem(decode_tc_kernel<4>, smem); if (rc) return rc;
-    decode_tc_kernel<4><<<grid, 512, smem, s>>>(map->d, a, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+    decode_tc_kernel<4><<<grid, 512, smem, s>>>(map->d, a, (const uint4*)map->dec_pack, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
   }
   BNV_LAUNCH_CHECK("decode_tc_kernel");
   return BNV_OK;

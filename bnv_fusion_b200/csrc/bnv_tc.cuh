@@ -53,6 +53,24 @@ __host__ __device__ inline WeightImage weight_image(int in_pad) {
   return w;
 }
 
+// ---- first-layer input order -------------------------------------------------------------------
+// Input-column order of the decoder's first layer as the tensor-core path feeds it.  The 17 inputs
+// [l(3) sin(3) cos(3) feat(8)] + 15 ones are permuted (W0's columns are permuted identically when the
+// weight image is packed) so that every fp16x2 word of a row depends on ONE axis or is a gathered
+// feature pair: [f0..f7 | lx sx cx 1 | ly sy cy 1 | lz sz cz 1 | 1 x 12].  The per-axis words exist in a
+// floor and a ceil flavour computed once per query; a corner row is then 4 gathered words + 6 selected
+// words + 6 constants -- no per-corner sincos / conversions.
+__host__ __device__ constexpr int dec_perm(int pos) {
+  return pos < 8 ? 9 + pos
+         : pos < 20 ? ((pos - 8) % 4 == 3 ? 17 + (pos - 8) / 4 : (pos - 8) / 4 + 3 * ((pos - 8) % 4))
+                    : pos;
+}
+// encoder: [x 1 | y 1 | z 1 | n0 n1 | n2 1 | 1 x 6]
+__host__ __device__ constexpr int enc_perm(int pos) {
+  return pos == 0 ? 0 : pos == 1 ? 6 : pos == 2 ? 1 : pos == 3 ? 7 : pos == 4 ? 2 : pos == 5 ? 8 : pos == 6 ? 3
+         : pos == 7 ? 4 : pos == 8 ? 5 : pos;
+}
+
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
