@@ -43,6 +43,9 @@ SIGNATURES = {
     "bnv_map_set_shard": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     "bnv_map_set_timing": (C.c_int, [_P, C.c_int]),
     "bnv_map_get_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "bnv_map_set_halo_buffer": (C.c_int, [_P, _P, _I64]),
+    "bnv_map_halo_begin": (C.c_int, [_P, _P]),
+    "bnv_map_insert_halo": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bnv_map_query": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P]),
     "bnv_map_insert": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "bnv_map_export": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),

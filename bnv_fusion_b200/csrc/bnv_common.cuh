@@ -66,8 +66,11 @@ struct MapDev {
   int32_t* fcnt;        // [fcap]
   int32_t* touched;     // [fcap] scratch rows in first-touch order
   int32_t fcap;
-  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] spare
+  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter
   int32_t* ctr;
+  // halo buffer of the tile shard (nullable): [int32 count, pad[9], records of 10 x 4 B]
+  int32_t* halo;
+  int32_t halo_cap;
 };
 
 __host__ __device__ inline bool owns(const GeomDev& g, int x) {

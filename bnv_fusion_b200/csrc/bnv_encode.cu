@@ -181,11 +181,27 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
         const float w_old = fresh ? 0.f : m.weights[slot];
         const float f_old = fresh ? 0.f : m.feats[(size_t)slot * kFeat + lane8];
         const float w = __fadd_rn(w_old, w_new);
-        m.feats[(size_t)slot * kFeat + lane8] = fuse_feat(f_old, w_old, mean, w_new, w);
+        const float f_new = fuse_feat(f_old, w_old, mean, w_new, w);
+        m.feats[(size_t)slot * kFeat + lane8] = f_new;
         __syncwarp(gmask);
         if (lane8 == 0) {
           m.weights[slot] = w;
           ++integrated;
+        }
+        if (m.halo && ((key / m.g.nyz) & ((1 << m.g.brick_log2) - 1)) == 0) {   // first x-plane of a brick
+          int pos = 0;
+          if (lane8 == 0) pos = atomicAdd(&m.halo[0], 1);
+          pos = __shfl_sync(gmask, pos, (threadIdx.x & 31) & ~7);
+          if (pos < m.halo_cap) {
+            int32_t* rec = m.halo + 10 + (size_t)pos * 10;
+            reinterpret_cast<float*>(rec)[2 + lane8] = f_new;
+            if (lane8 == 0) {
+              rec[0] = key;
+              reinterpret_cast<float*>(rec)[1] = w;
+            }
+          } else if (lane8 == 0) {
+            atomicOr(&m.ctr[2], kErrCapacity);
+          }
         }
       }
     }

@@ -160,11 +160,70 @@ __global__ void count_optim_apply_kernel(int32_t* __restrict__ flags, float* __r
   }
 }
 
+// upsert the halo records of the other ranks that this rank needs: 8 lanes per record
+__global__ void insert_halo_kernel(MapDev m, const int32_t* __restrict__ gathered, int world, int64_t cap) {
+  const int64_t stride_words = 10 + cap * 10;
+  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
+  const int lane8 = threadIdx.x & 7;
+  for (int r = 0; r < world; ++r) {
+    if (r == m.g.rank) continue;
+    const int32_t* buf = gathered + r * stride_words;
+    const int n = min(buf[0], (int)cap);
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n;
+         i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+      const int32_t* rec = buf + 10 + i * 10;
+      const int32_t flat = rec[0];
+      const int x = flat / m.g.nyz;
+      const bool need = x >= 1 && ((x - 1) >> m.g.brick_log2) % m.g.world == m.g.rank;
+      int32_t slot = -1;
+      if (need && lane8 == 0) {
+        slot = m.table[flat];
+        if (slot < 0) {                      // keys are unique within one rank's buffer and across ranks
+          slot = atomicAdd(&m.ctr[0], 1);
+          if (slot < m.cap) {
+            m.table[flat] = slot;
+            m.keys[slot] = flat;
+            m.hits[slot] = 0.f;
+          } else {
+            atomicOr(&m.ctr[2], kErrCapacity);
+            slot = -1;
+          }
+        }
+      }
+      slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) & ~7);
+      if (slot >= 0) {
+        m.feats[(size_t)slot * kFeat + lane8] = reinterpret_cast<const float*>(rec)[2 + lane8];
+        if (lane8 == 0) m.weights[slot] = reinterpret_cast<const float*>(rec)[1];
+      }
+    }
+  }
+}
+
 }  // namespace bnv
 
 using namespace bnv;
 
 extern "C" {
+
+int bnv_map_set_halo_buffer(bnv_map_t* m, void* buf, int64_t cap) {
+  if (!m || cap < 0 || cap > 0x7fffffff) { set_error("bnv_map_set_halo_buffer: bad argument"); return BNV_E_ARG; }
+  m->d.halo = (int32_t*)buf;
+  m->d.halo_cap = buf ? (int32_t)cap : 0;
+  return BNV_OK;
+}
+
+int bnv_map_halo_begin(bnv_map_t* m, void* stream) {
+  if (!m || !m->d.halo) { set_error("bnv_map_halo_begin: no halo buffer attached"); return BNV_E_ARG; }
+  BNV_CUDA(cudaMemsetAsync(m->d.halo, 0, 40, (cudaStream_t)stream));
+  return BNV_OK;
+}
+
+int bnv_map_insert_halo(bnv_map_t* m, const void* gathered, int world, int64_t cap, void* stream) {
+  if (!m || !gathered || world != m->d.g.world || cap <= 0) { set_error("bnv_map_insert_halo: bad argument"); return BNV_E_ARG; }
+  insert_halo_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(m->d, (const int32_t*)gathered, world, cap);
+  BNV_LAUNCH_CHECK("insert_halo_kernel");
+  return BNV_OK;
+}
 
 int bnv_abi_version(void) { return BNV_ABI_VERSION; }
 const char* bnv_last_error(void) { return g_err; }

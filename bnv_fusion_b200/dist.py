@@ -1,0 +1,105 @@
+"""Tile shard of the voxel grid over the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference is single-GPU (no torch.distributed / NCCL call sites); this is the
+B200-side extension the north star asks for: ownership is a pure function of the voxel's x index,
+
+    owner(x) = (x >> brick_log2) % world        (x-bricks of 2^brick_log2 voxels, round-robin)
+
+Every rank receives the whole depth frame and runs the same fused encode kernel, which drops the
+(point, corner) rows whose voxel it does not own *before* the MLP, so the tensor-core work divides
+by `world` while per-voxel means stay identical to the single-GPU result (all rows of a voxel go to
+its one owner: no cross-GPU reduction).  A query's 8 corners are floor/ceil voxels, so the owner of
+brick b also needs the first x-plane of brick b+1: after each frame the ranks all-gather the records
+of the boundary voxels they integrated (ONE collective per frame, fixed-capacity buffer with the
+count in its header) and upsert the ones they need as halo copies.
+
+The buffer protocol and the selection rule live in plain numpy functions so that the N > 1 logic is
+covered on CPU with gloo (tests/test_dist_cpu.py); the GPU path calls the same rule inside
+libbnv_b200 (bnv_map_insert_halo).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+HEADER_WORDS = 10          # int32 [count, pad x 9]
+RECORD_WORDS = 10          # int32 flat_id, float32 weight, float32 feat[8]
+
+
+def owner_of_x(x, world, brick_log2):
+    return (np.asarray(x) >> brick_log2) % world
+
+
+def is_boundary_x(x, brick_log2):
+    """first x-plane of a brick: the voxels the previous brick's owner needs as ceil corners"""
+    return (np.asarray(x) & ((1 << brick_log2) - 1)) == 0
+
+
+def pack_halo(flat, weights, feats, capacity):
+    """records -> int32 buffer [count, pad, records...] of fixed capacity"""
+    n = len(flat)
+    if n > capacity:
+        raise RuntimeError(f"halo buffer overflow: {n} > {capacity}")
+    buf = np.zeros(HEADER_WORDS + capacity * RECORD_WORDS, np.int32)
+    buf[0] = n
+    rec = buf[HEADER_WORDS:].reshape(capacity, RECORD_WORDS)
+    rec[:n, 0] = np.asarray(flat, np.int32)
+    rec[:n, 1] = np.asarray(weights, np.float32).view(np.int32)
+    rec[:n, 2:] = np.asarray(feats, np.float32).reshape(n, 8).view(np.int32)
+    return buf
+
+
+def unpack_gathered(gathered, world, capacity):
+    """all-gathered int32 buffer -> per-rank (flat, weights, feats)"""
+    g = np.asarray(gathered, np.int32).reshape(world, HEADER_WORDS + capacity * RECORD_WORDS)
+    out = []
+    for r in range(world):
+        n = int(g[r, 0])
+        rec = g[r, HEADER_WORDS:].reshape(capacity, RECORD_WORDS)[:n]
+        out.append((rec[:, 0].astype(np.int64), rec[:, 1].copy().view(np.float32), rec[:, 2:].copy().view(np.float32)))
+    return out
+
+
+def select_needed(flat, n_xyz, rank, world, brick_log2):
+    """mask of gathered records this rank needs: owner(x - 1) == rank (x >= 1)"""
+    x = np.asarray(flat, np.int64) // (int(n_xyz[1]) * int(n_xyz[2]))
+    return (x >= 1) & (owner_of_x(np.maximum(x - 1, 0), world, brick_log2) == rank)
+
+
+class TileShardedFusion:
+    """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
+
+    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 17, group=None):
+        import torch
+        from . import _lib
+        self.torch, self._lib = torch, _lib
+        self.volume, self.model = volume, model
+        self.rank, self.world, self.brick_log2 = int(rank), int(world), int(brick_log2)
+        self.capacity = int(halo_capacity)
+        self.group = group
+        words = HEADER_WORDS + self.capacity * RECORD_WORDS
+        dev = volume.device
+        self.halo = torch.zeros(words, dtype=torch.int32, device=dev)
+        self.gathered = torch.zeros(words * self.world, dtype=torch.int32, device=dev)
+        volume.set_shard(self.rank, self.world, self.brick_log2)
+        _lib.check(volume._lib.bnv_map_set_halo_buffer(volume._handle, _lib.ptr(self.halo), self.capacity),
+                   "bnv_map_set_halo_buffer")
+
+    def fuse_depth_frame(self, depth_mm, K, T_wc, max_depth=3.0, stats=None, navg=None):
+        import torch.distributed as dist
+        v, lib = self.volume, self._lib
+        lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
+        self.model.fuse_depth_frame(v, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.halo, group=self.group)   # the one collective
+            lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered), self.world, self.capacity,
+                                                 v._stream()), "bnv_map_insert_halo")
+
+    def owned_rows(self):
+        """bool mask over the rows of volume.to_tensor(): voxels this rank owns (not halo copies)"""
+        x = self.volume.active_coordinates[:, 0]
+        return ((x >> self.brick_log2) % self.world) == self.rank
+
+    def detach(self):
+        self._lib.check(self.volume._lib.bnv_map_set_halo_buffer(self.volume._handle, None, 0), "detach halo")

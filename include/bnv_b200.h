@@ -90,6 +90,21 @@ int bnv_map_status(bnv_map_t* map, void* stream);
  * Encode calls drop (point, corner) rows whose voxel another rank owns.  world = 1 disables. */
 int bnv_map_set_shard(bnv_map_t* map, int rank, int world, int brick_log2);
 
+/* Halo exchange of the tile shard (no reference equivalent: the reference is single-GPU).  A query's
+ * 8 corners are floor/ceil voxels, so the owner of brick b also needs the first x-plane of brick b+1.
+ * With a halo buffer attached, bnv_fuse_frame / bnv_fuse_points append one record per voxel they
+ * integrated whose x is the first plane of a brick (x % 2^brick_log2 == 0):
+ *     struct { int32 flat_id; float weight; float feat[8]; }   (40 bytes)
+ * into buf_dev = [int32 count, int32 pad[9], records...] (capacity records).  The caller all-gathers
+ * the ranks' buffers (one NCCL all-gather per frame) and hands the result to bnv_map_insert_halo,
+ * which upserts the records of the other ranks that this rank needs (owner(x-1) == rank).
+ * bnv_map_halo_begin resets the count (stream-ordered).  buf_dev == NULL detaches. */
+#define BNV_HALO_RECORD_BYTES 40
+int bnv_map_set_halo_buffer(bnv_map_t* map, void* buf_dev, int64_t capacity_records);
+int bnv_map_halo_begin(bnv_map_t* map, void* stream);
+int bnv_map_insert_halo(bnv_map_t* map, const void* gathered_dev, int world, int64_t capacity_records,
+                        void* stream);
+
 /* SparseVolume.query (sparse_volume.py:661-695): coords_dev [n,3] int64 -> feats [n,F], weights [n],
  * num_hits [n] (zeros for misses), found [n] uint8 (nullable). */
 int bnv_map_query(bnv_map_t* map, const int64_t* coords_dev, int64_t n, float* feats_dev,

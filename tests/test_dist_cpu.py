@@ -1,0 +1,134 @@
+"""CPU, gloo, world_size 2: the tile-shard logic (ownership, one all-gather per frame of boundary
+records, halo selection) on top of the numpy oracle.  The union of the ranks' owned voxels must equal
+the single-process map bit for bit, and every rank must hold the halo voxels its own queries need."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import bnv_oracle as O          # noqa: E402
+from bnv_fusion_b200 import dist as D      # noqa: E402
+from bnv_fusion_b200 import synth          # noqa: E402
+
+BRICK = 2      # 4-voxel bricks so that the 32^3 test grid has several bricks per rank
+CAP = 4096
+N_FRAMES = 10
+
+
+def _sharded_encode(pts6, grid, enc, rank, world):
+    """encode_pointcloud restricted to the (point, corner) rows whose voxel this rank owns"""
+    rows = O.encode_rows(pts6, grid)
+    if not rows["keep"].any():
+        return None
+    x = rows["mlp_in"].reshape(-1, 6)
+    flat = rows["flat"].reshape(-1)
+    mine = D.owner_of_x(rows["corner_ijk"][..., 0].reshape(-1), world, BRICK) == rank
+    x, flat = x[mine], flat[mine]
+    if flat.size == 0:
+        return None
+    f = O.mlp_forward(enc, x, 6, 8)
+    uniq, inv, cnt = np.unique(flat, return_inverse=True, return_counts=True)
+    sums = np.zeros((uniq.size, 8))
+    np.add.at(sums, inv, f.astype(np.float64))
+    mean = (sums / cnt[:, None]).astype(np.float32)
+    ok = cnt >= 8
+    return mean[ok], cnt[ok], uniq[ok]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
+    spec = synth.stream_spec("parity64")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vm = O.VoxelMap(grid)
+    nyz = grid.n_xyz[1] * grid.n_xyz[2]
+    for fi in range(N_FRAMES):
+        d, K, T = synth.make_frame(spec, fi, seed=0)
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        res = _sharded_encode(O.backproject(depth, mask, K, T), grid, p["encoder"], rank, world)
+        flat = np.zeros(0, np.int64)
+        if res is not None:
+            feats, cnt, flat = res
+            O.integrate(vm, flat, feats, cnt)
+        # boundary records integrated this frame -> ONE all-gather -> upsert what this rank needs
+        b = flat[D.is_boundary_x(flat // nyz, BRICK)]
+        f, w, _, _ = vm.query(b)
+        mine = torch.from_numpy(D.pack_halo(b, w, f, CAP))
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        per_rank = D.unpack_gathered(torch.cat(gathered).numpy(), world, CAP)
+        for r, (hf, hw, hfeat) in enumerate(per_rank):
+            if r == rank:
+                continue
+            need = D.select_needed(hf, grid.n_xyz, rank, world, BRICK)
+            vm.insert(hf[need], hfeat[need], hw[need], np.zeros(int(need.sum()), np.float32))
+    keys = np.fromiter(vm.index.keys(), dtype=np.int64)
+    f, w, _, _ = vm.query(keys)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), keys=keys, feats=f, weights=w)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tile_shard_world2(tmp_path, tcnn_params):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    # single-process reference
+    spec = synth.stream_spec("parity64")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    ref = O.VoxelMap(grid)
+    for fi in range(N_FRAMES):
+        d, K, T = synth.make_frame(spec, fi, seed=0)
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        feats, counts, flat, _, _, _ = O.encode_pointcloud(O.backproject(depth, mask, K, T), grid, tcnn_params["encoder"], 8)
+        O.integrate(ref, flat, feats, counts)
+    ref_keys = np.sort(np.fromiter(ref.index.keys(), dtype=np.int64))
+    nyz = grid.n_xyz[1] * grid.n_xyz[2]
+    owned_all = []
+    for rank in range(world):
+        z = np.load(os.path.join(str(tmp_path), f"rank{rank}.npz"))
+        keys, feats, weights = z["keys"], z["feats"], z["weights"]
+        x = keys // nyz
+        own = D.owner_of_x(x, world, BRICK) == rank
+        owned_all.append(keys[own])
+        # every voxel this rank holds (owned or halo) carries exactly the single-process values
+        f_ref, w_ref, _, found = ref.query(keys)
+        assert found.all()
+        assert np.array_equal(feats, f_ref) and np.array_equal(weights, w_ref)
+        # halo completeness: the ceil-neighbour plane of every owned brick is present when it exists
+        held = set(keys.tolist())
+        for k in ref_keys:
+            xk = k // nyz
+            if xk >= 1 and D.owner_of_x(xk - 1, world, BRICK) == rank and D.is_boundary_x(xk, BRICK):
+                assert int(k) in held, (rank, int(k))
+        # no foreign voxels beyond the halo planes
+        foreign = keys[~own]
+        assert D.is_boundary_x(foreign // nyz, BRICK).all()
+    union = np.sort(np.concatenate(owned_all))
+    assert np.array_equal(union, ref_keys)          # disjoint cover of the single-process map
+
+
+def test_halo_buffer_protocol():
+    rng = np.random.default_rng(0)
+    flat = rng.choice(32 ** 3, 100, replace=False)
+    w = rng.random(100).astype(np.float32)
+    f = rng.standard_normal((100, 8)).astype(np.float32)
+    buf = D.pack_halo(flat, w, f, 256)
+    assert buf.dtype == np.int32 and buf.size == D.HEADER_WORDS + 256 * D.RECORD_WORDS and buf[0] == 100
+    (f2, w2, ft2), (e0, e1, e2) = D.unpack_gathered(np.concatenate([buf, D.pack_halo([], [], np.zeros((0, 8)), 256)]), 2, 256)
+    assert np.array_equal(f2, flat) and np.array_equal(w2, w) and np.array_equal(ft2, f) and e0.size == 0
+    with pytest.raises(RuntimeError):
+        D.pack_halo(flat, w, f, 10)
+    x = np.arange(64)
+    assert np.array_equal(D.owner_of_x(x, 4, 2), (x // 4) % 4)
+    need = D.select_needed(np.array([0, 4 * 1024, 8 * 1024, 5 * 1024]), (32, 32, 32), 0, 2, 2)
+    # x = 0: no x-1; x = 4: x-1 = 3 in brick 0 (rank 0); x = 8: x-1 = 7 in brick 1 (rank 1); x = 5: x-1 = 4 (rank 1)
+    assert need.tolist() == [False, True, False, False]
