@@ -45,7 +45,7 @@ struct GeomDev {
   int32_t n[3];
   int32_t nyz;          // n[1]*n[2]
   int64_t n_vox;
-  // tile shard (multi-GPU): owner(x) = (x >> brick_log2) % world
+  // tile shard (multi-GPU): owner(x,y,z) = ((x >> b) + (y >> b) + (z >> b)) % world  (3-D brick checkerboard)
   int32_t rank, world, brick_log2;
 };
 
@@ -73,8 +73,28 @@ struct MapDev {
   int32_t halo_cap;
 };
 
-__host__ __device__ inline bool owns(const GeomDev& g, int x) {
-  return g.world <= 1 || ((x >> g.brick_log2) % g.world) == g.rank;
+__host__ __device__ inline int owner_of(const GeomDev& g, int x, int y, int z) {
+  return ((x >> g.brick_log2) + (y >> g.brick_log2) + (z >> g.brick_log2)) % g.world;
+}
+__host__ __device__ inline bool owns(const GeomDev& g, int x, int y, int z) {
+  return g.world <= 1 || owner_of(g, x, y, z) == g.rank;
+}
+// voxel on the outer shell of its brick: some rank other than its owner may need it as a corner
+__host__ __device__ inline bool on_brick_shell(const GeomDev& g, int x, int y, int z) {
+  const int m = (1 << g.brick_log2) - 1;
+  const int a = x & m, b = y & m, c = z & m;
+  return a == 0 || a == m || b == 0 || b == m || c == 0 || c == m;
+}
+// does `rank` own a brick that touches voxel (x,y,z) (26-neighbourhood) ?
+__host__ __device__ inline bool rank_touches(const GeomDev& g, int x, int y, int z, int rank) {
+  for (int dx = -1; dx <= 1; ++dx)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dz = -1; dz <= 1; ++dz) {
+        const int u = x + dx, v = y + dy, w = z + dz;
+        if (u < 0 || v < 0 || w < 0 || u >= g.n[0] || v >= g.n[1] || w >= g.n[2]) continue;
+        if (owner_of(g, u, v, w) == rank) return true;
+      }
+  return false;
 }
 
 }  // namespace bnv

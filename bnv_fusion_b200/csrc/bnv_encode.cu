@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_simt_kernel(MapDev m, EncS
       const int cz = (k == 3 || k == 5 || k == 6 || k == 7);
       const float nb[3] = {cx ? ce[0] : fl[0], cy ? ce[1] : fl[1], cz ? ce[2] : fl[2]};
       const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-      if (!owns(g, ix)) continue;
+      if (!owns(g, ix, iy, iz)) continue;
       float x[6], y[8];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
           m.weights[slot] = w;
           ++integrated;
         }
-        if (m.halo && ((key / m.g.nyz) & ((1 << m.g.brick_log2) - 1)) == 0) {   // first x-plane of a brick
+        const int kx = key / m.g.nyz, kr = key - kx * m.g.nyz, ky = kr / m.g.n[2], kz = kr - ky * m.g.n[2];
+        if (m.halo && on_brick_shell(m.g, kx, ky, kz)) {            // another rank may need it as a corner
           int pos = 0;
           if (lane8 == 0) pos = atomicAdd(&m.halo[0], 1);
           pos = __shfl_sync(gmask, pos, (threadIdx.x & 31) & ~7);

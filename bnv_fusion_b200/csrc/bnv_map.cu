@@ -173,8 +173,8 @@ __global__ void insert_halo_kernel(MapDev m, const int32_t* __restrict__ gathere
          i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
       const int32_t* rec = buf + 10 + i * 10;
       const int32_t flat = rec[0];
-      const int x = flat / m.g.nyz;
-      const bool need = x >= 1 && ((x - 1) >> m.g.brick_log2) % m.g.world == m.g.rank;
+      const int x = flat / m.g.nyz, rr = flat - x * m.g.nyz, y = rr / m.g.n[2], z = rr - y * m.g.n[2];
+      const bool need = rank_touches(m.g, x, y, z, m.g.rank);
       int32_t slot = -1;
       if (need && lane8 == 0) {
         slot = m.table[flat];

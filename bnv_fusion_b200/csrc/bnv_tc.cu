@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       corner_of(k, fl, ce, nb);
       const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
       slot[k] = -1;
-      if (inb && owns(g, ix)) {
+      if (inb && owns(g, ix, iy, iz)) {
         slot[k] = claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
         ++n_rows;
       }

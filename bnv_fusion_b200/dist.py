@@ -1,16 +1,18 @@
 """Tile shard of the voxel grid over the GPUs of one box (one process per GPU, torch.distributed).
 
 The reference is single-GPU (no torch.distributed / NCCL call sites); this is the
-B200-side extension the north star asks for: ownership is a pure function of the voxel's x index,
+B200-side extension the north star asks for: ownership is a pure function of the voxel coordinate,
 
-    owner(x) = (x >> brick_log2) % world        (x-bricks of 2^brick_log2 voxels, round-robin)
+    owner(x, y, z) = ((x >> b) + (y >> b) + (z >> b)) % world     (3-D checkerboard of 2^b bricks;
+                                                                    balanced for planar surfaces
+                                                                    along any axis)
 
 Every rank receives the whole depth frame and runs the same fused encode kernel, which drops the
 (point, corner) rows whose voxel it does not own *before* the MLP, so the tensor-core work divides
 by `world` while per-voxel means stay identical to the single-GPU result (all rows of a voxel go to
-its one owner: no cross-GPU reduction).  A query's 8 corners are floor/ceil voxels, so the owner of
-brick b also needs the first x-plane of brick b+1: after each frame the ranks all-gather the records
-of the boundary voxels they integrated (ONE collective per frame, fixed-capacity buffer with the
+its one owner: no cross-GPU reduction).  A query's 8 corners are floor/ceil voxels and meshlize samples
+id +- 0.5, so a rank also needs the one-voxel shell around its bricks: after each frame the ranks
+all-gather the records of the brick-shell voxels they integrated (ONE collective per frame, fixed-capacity buffer with the
 count in its header) and upsert the ones they need as halo copies.
 
 The buffer protocol and the selection rule live in plain numpy functions so that the N > 1 logic is
@@ -27,13 +29,26 @@ HEADER_WORDS = 10          # int32 [count, pad x 9]
 RECORD_WORDS = 10          # int32 flat_id, float32 weight, float32 feat[8]
 
 
-def owner_of_x(x, world, brick_log2):
-    return (np.asarray(x) >> brick_log2) % world
+def owner_of(ijk, world, brick_log2):
+    """3-D brick checkerboard: ((x >> b) + (y >> b) + (z >> b)) % world for int coords [..., 3]"""
+    ijk = np.asarray(ijk, np.int64)
+    return ((ijk[..., 0] >> brick_log2) + (ijk[..., 1] >> brick_log2) + (ijk[..., 2] >> brick_log2)) % world
 
 
-def is_boundary_x(x, brick_log2):
-    """first x-plane of a brick: the voxels the previous brick's owner needs as ceil corners"""
-    return (np.asarray(x) & ((1 << brick_log2) - 1)) == 0
+def on_brick_shell(ijk, brick_log2):
+    """voxels on the outer shell of their brick: some other rank may need them as a decode corner"""
+    m = (1 << brick_log2) - 1
+    a = np.asarray(ijk, np.int64) & m
+    return ((a == 0) | (a == m)).any(axis=-1)
+
+
+def unflatten(flat, n_xyz):
+    flat = np.asarray(flat, np.int64)
+    nyz = int(n_xyz[1]) * int(n_xyz[2])
+    x = flat // nyz
+    r = flat - x * nyz
+    y = r // int(n_xyz[2])
+    return np.stack([x, y, r - y * int(n_xyz[2])], axis=-1)
 
 
 def pack_halo(flat, weights, feats, capacity):
@@ -62,9 +77,17 @@ def unpack_gathered(gathered, world, capacity):
 
 
 def select_needed(flat, n_xyz, rank, world, brick_log2):
-    """mask of gathered records this rank needs: owner(x - 1) == rank (x >= 1)"""
-    x = np.asarray(flat, np.int64) // (int(n_xyz[1]) * int(n_xyz[2]))
-    return (x >= 1) & (owner_of_x(np.maximum(x - 1, 0), world, brick_log2) == rank)
+    """mask of gathered records this rank needs: it owns a brick touching the voxel (26-neighbourhood)"""
+    ijk = unflatten(flat, n_xyz)
+    need = np.zeros(len(ijk), bool)
+    n = np.asarray(n_xyz, np.int64)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                q = ijk + np.array([dx, dy, dz])
+                inside = ((q >= 0) & (q < n)).all(axis=-1)
+                need |= inside & (owner_of(np.clip(q, 0, n - 1), world, brick_log2) == rank)
+    return need
 
 
 class TileShardedFusion:
@@ -98,8 +121,8 @@ class TileShardedFusion:
 
     def owned_rows(self):
         """bool mask over the rows of volume.to_tensor(): voxels this rank owns (not halo copies)"""
-        x = self.volume.active_coordinates[:, 0]
-        return ((x >> self.brick_log2) % self.world) == self.rank
+        c = self.volume.active_coordinates >> self.brick_log2
+        return (c.sum(dim=1) % self.world) == self.rank
 
     def detach(self):
         self._lib.check(self.volume._lib.bnv_map_set_halo_buffer(self.volume._handle, None, 0), "detach halo")

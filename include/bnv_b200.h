@@ -86,18 +86,19 @@ int bnv_map_reset(bnv_map_t* map, void* stream);
 /* Number of active voxels and latched device-side status.  Host sync on `stream`. */
 int bnv_map_size(bnv_map_t* map, int64_t* n_active_host, void* stream);
 int bnv_map_status(bnv_map_t* map, void* stream);
-/* Tile ownership for the multi-GPU shard: a voxel belongs to rank ((x >> brick_log2) % world).
+/* Tile ownership for the multi-GPU shard: 3-D checkerboard of 2^brick_log2 bricks, a voxel belongs to
+ * rank ((x >> b) + (y >> b) + (z >> b)) % world.
  * Encode calls drop (point, corner) rows whose voxel another rank owns.  world = 1 disables. */
 int bnv_map_set_shard(bnv_map_t* map, int rank, int world, int brick_log2);
 
 /* Halo exchange of the tile shard (no reference equivalent: the reference is single-GPU).  A query's
- * 8 corners are floor/ceil voxels, so the owner of brick b also needs the first x-plane of brick b+1.
- * With a halo buffer attached, bnv_fuse_frame / bnv_fuse_points append one record per voxel they
- * integrated whose x is the first plane of a brick (x % 2^brick_log2 == 0):
+ * 8 corners are floor/ceil voxels and meshlize samples id +- 0.5, so a rank also needs the one-voxel
+ * shell around each of its bricks.  With a halo buffer attached, bnv_fuse_frame / bnv_fuse_points
+ * append one record per voxel they integrated that lies on the outer shell of its brick:
  *     struct { int32 flat_id; float weight; float feat[8]; }   (40 bytes)
  * into buf_dev = [int32 count, int32 pad[9], records...] (capacity records).  The caller all-gathers
  * the ranks' buffers (one NCCL all-gather per frame) and hands the result to bnv_map_insert_halo,
- * which upserts the records of the other ranks that this rank needs (owner(x-1) == rank).
+  * which upserts the records of the other ranks that touch one of this rank's bricks.
  * bnv_map_halo_begin resets the count (stream-ordered).  buf_dev == NULL detaches. */
 #define BNV_HALO_RECORD_BYTES 40
 int bnv_map_set_halo_buffer(bnv_map_t* map, void* buf_dev, int64_t capacity_records);

@@ -29,7 +29,7 @@ def _sharded_encode(pts6, grid, enc, rank, world):
         return None
     x = rows["mlp_in"].reshape(-1, 6)
     flat = rows["flat"].reshape(-1)
-    mine = D.owner_of_x(rows["corner_ijk"][..., 0].reshape(-1), world, BRICK) == rank
+    mine = D.owner_of(rows["corner_ijk"].reshape(-1, 3), world, BRICK) == rank
     x, flat = x[mine], flat[mine]
     if flat.size == 0:
         return None
@@ -59,7 +59,7 @@ def _worker(rank, world, port, out_dir):
             feats, cnt, flat = res
             O.integrate(vm, flat, feats, cnt)
         # boundary records integrated this frame -> ONE all-gather -> upsert what this rank needs
-        b = flat[D.is_boundary_x(flat // nyz, BRICK)]
+        b = flat[D.on_brick_shell(D.unflatten(flat, grid.n_xyz), BRICK)]
         f, w, _, _ = vm.query(b)
         mine = torch.from_numpy(D.pack_halo(b, w, f, CAP))
         gathered = [torch.zeros_like(mine) for _ in range(world)]
@@ -96,22 +96,27 @@ def test_tile_shard_world2(tmp_path, tcnn_params):
     for rank in range(world):
         z = np.load(os.path.join(str(tmp_path), f"rank{rank}.npz"))
         keys, feats, weights = z["keys"], z["feats"], z["weights"]
-        x = keys // nyz
-        own = D.owner_of_x(x, world, BRICK) == rank
+        ijk = D.unflatten(keys, grid.n_xyz)
+        own = D.owner_of(ijk, world, BRICK) == rank
         owned_all.append(keys[own])
         # every voxel this rank holds (owned or halo) carries exactly the single-process values
         f_ref, w_ref, _, found = ref.query(keys)
         assert found.all()
         assert np.array_equal(feats, f_ref) and np.array_equal(weights, w_ref)
-        # halo completeness: the ceil-neighbour plane of every owned brick is present when it exists
+        # halo completeness: every map voxel within one voxel of an owned voxel is present
         held = set(keys.tolist())
-        for k in ref_keys:
-            xk = k // nyz
-            if xk >= 1 and D.owner_of_x(xk - 1, world, BRICK) == rank and D.is_boundary_x(xk, BRICK):
-                assert int(k) in held, (rank, int(k))
-        # no foreign voxels beyond the halo planes
-        foreign = keys[~own]
-        assert D.is_boundary_x(foreign // nyz, BRICK).all()
+        rijk = D.unflatten(ref_keys, grid.n_xyz)
+        need = D.select_needed(ref_keys, grid.n_xyz, rank, world, BRICK)
+        assert set(ref_keys[need].tolist()) <= held
+        for k in keys[own][:200]:
+            kk = D.unflatten([k], grid.n_xyz)[0]
+            for d in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1), (1, 1, 1), (-1, -1, -1)):
+                q = kk + np.array(d)
+                fq = int(q[0] * nyz + q[1] * grid.n_xyz[2] + q[2])
+                if fq in ref.index:
+                    assert fq in held, (rank, kk, d)
+        # no foreign voxels beyond the brick shells
+        assert D.on_brick_shell(ijk[~own], BRICK).all()
     union = np.sort(np.concatenate(owned_all))
     assert np.array_equal(union, ref_keys)          # disjoint cover of the single-process map
 
@@ -127,8 +132,11 @@ def test_halo_buffer_protocol():
     assert np.array_equal(f2, flat) and np.array_equal(w2, w) and np.array_equal(ft2, f) and e0.size == 0
     with pytest.raises(RuntimeError):
         D.pack_halo(flat, w, f, 10)
-    x = np.arange(64)
-    assert np.array_equal(D.owner_of_x(x, 4, 2), (x // 4) % 4)
-    need = D.select_needed(np.array([0, 4 * 1024, 8 * 1024, 5 * 1024]), (32, 32, 32), 0, 2, 2)
-    # x = 0: no x-1; x = 4: x-1 = 3 in brick 0 (rank 0); x = 8: x-1 = 7 in brick 1 (rank 1); x = 5: x-1 = 4 (rank 1)
-    assert need.tolist() == [False, True, False, False]
+    ijk = np.array([[0, 0, 0], [4, 0, 0], [4, 4, 0], [5, 5, 5], [7, 1, 1]])
+    assert D.owner_of(ijk, 2, 2).tolist() == [0, 1, 0, 1, 1]
+    assert D.on_brick_shell(ijk, 2).tolist() == [True, True, True, False, True]
+    flat = ijk[:, 0] * 1024 + ijk[:, 1] * 32 + ijk[:, 2]
+    assert np.array_equal(D.unflatten(flat, (32, 32, 32)), ijk)
+    # (5,5,5) sits inside brick (1,1,1) (rank 1): only rank 1 touches it; (4,0,0) touches brick (0,0,0) of rank 0
+    assert D.select_needed(flat, (32, 32, 32), 0, 2, 2).tolist() == [True, True, True, False, True]
+    assert D.select_needed(flat, (32, 32, 32), 1, 2, 2).tolist() == [False, True, True, True, True]
