@@ -41,6 +41,13 @@ SIGNATURES = {
     "bnv_map_size": (C.c_int, [_P, C.POINTER(_I64), _P]),
     "bnv_map_status": (C.c_int, [_P, _P]),
     "bnv_map_set_shard": (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
+    "bnv_tsdf_create": (C.c_int, [C.POINTER(_P), _P, C.c_double, C.c_int]),
+    "bnv_tsdf_destroy": (C.c_int, [_P]),
+    "bnv_tsdf_dims": (C.c_int, [_P, _P]),
+    "bnv_tsdf_integrate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_double, _P]),
+    "bnv_tsdf_volume": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "bnv_tsdf_copy": (C.c_int, [_P, C.c_int, _P, _P]),
+    "bnv_tsdf_prior": (C.c_int, [_P, C.c_double, C.c_double, _P, _P]),
     "bnv_map_set_timing": (C.c_int, [_P, C.c_int]),
     "bnv_map_get_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bnv_map_set_halo_buffer": (C.c_int, [_P, _P, _I64]),

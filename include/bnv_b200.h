@@ -184,6 +184,28 @@ int bnv_decode_voxel_blocks(bnv_map_t* map, int64_t first, int64_t count, const 
                             int min_pts, int mode, const float* tsdf_delta_dev,
                             const int32_t* tsdf_dims_host, float* out_sdf_dev, void* stream);
 
+/* ---- coarse TSDF prior -------------------------------------------------
+ * Replaces third_parties/fusion.py TSDFVolume (constructor :22-167, integrate :208-294 -- CPU mode
+ * semantics, the reference's PyCUDA kernel :68-141 re-uploads both images per launch -- get_volume
+ * :296-300) and NeuralMap.prepare_tsdf_volume (src/run_e2e.py:169-186).  The volume lives on the device.
+ * vol_bnds_host = {x0,x1,y0,y1,z0,z1} metres (fusion.py's (3,2) array, row-major). */
+typedef struct bnv_tsdf bnv_tsdf_t;
+int bnv_tsdf_create(bnv_tsdf_t** out, const double* vol_bnds_host, double voxel_size, int device);
+int bnv_tsdf_destroy(bnv_tsdf_t* tsdf);
+int bnv_tsdf_dims(const bnv_tsdf_t* tsdf, int32_t* dims_host);
+/* integrate(color_im, depth_im, cam_intr, cam_pose, obs_weight): rgb_dev [H,W,3] float32 0..255 (nullable:
+ * skip the colour average); depth_dev [H,W] float32 metres, or uint16 millimetres when depth_is_u16_mm;
+ * K_host [9]; Tinv_host [12] = rows 0..2 of inv(cam_pose) in float32 (np.linalg.inv, fusion.py:254). */
+int bnv_tsdf_integrate(bnv_tsdf_t* tsdf, const float* rgb_dev, const void* depth_dev, int depth_is_u16_mm, int H,
+                       int W, const float* K_host, const float* Tinv_host, double obs_weight, void* stream);
+/* get_volume(): device pointers of the resident [Tx,Ty,Tz] float32 volumes (any may be NULL). */
+int bnv_tsdf_volume(bnv_tsdf_t* tsdf, float** tsdf_dev, float** color_dev, float** weight_dev);
+/* Snapshot of one volume into caller memory: which = 0 tsdf, 1 colour, 2 weight; out_dev [Tx,Ty,Tz] float32. */
+int bnv_tsdf_copy(bnv_tsdf_t* tsdf, int which, float* out_dev, void* stream);
+/* prepare_tsdf_volume: out = clip(tsdf * (voxel_size * 5), +-truncated_dist) * sdf_delta_weight, the array
+ * bnv_decode_sdf takes as tsdf_delta_dev.  out_dev == NULL writes an internal buffer (see bnv_tsdf_volume). */
+int bnv_tsdf_prior(bnv_tsdf_t* tsdf, double truncated_dist, double sdf_delta_weight, float* out_dev, void* stream);
+
 /* Per-kernel device timing for bench.py's roofline: when enabled, bnv_fuse_frame / bnv_fuse_points
  * record CUDA events on `stream` around the encode kernel and the finalize kernel.
  * bnv_map_get_timing waits for the last recorded call (host sync) and returns both durations. */
