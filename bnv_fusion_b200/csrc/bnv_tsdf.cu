@@ -92,7 +92,7 @@ __global__ void tsdf_prior_kernel(const float* __restrict__ tsdf, int64_t n, dou
                                   float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = (float)((double)tsdf[i] * scale);
+  float v = __fmul_rn(tsdf[i], (float)scale);     // float32 array * python float: float32 multiply
   v = fminf(fmaxf(v, -lim), lim);
   out[i] = __fmul_rn(v, wgt);
 }
