@@ -254,6 +254,28 @@ def run_b200(args):
     e2e_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
     vol.check_status()
+    # ---- reference "local" timer scope: neural fusion + coarse TSDF prior (run_e2e.py:78-109) -----------
+    from bnv_fusion_b200.tsdf import TSDFVolume
+    from bnv_fusion_b200.volume import get_world_range
+    mn, mx, _ = get_world_range(spec.dimensions, 0.025)               # run_e2e.py:62-71: fixed 2.5 cm
+    tsdf = TSDFVolume(np.stack([mn, mx], 1), 0.025, device=dev)
+    def step_local(i):
+        _, K, T = frames[i % N_FRAMES]
+        stage.copy_(host[i % N_FRAMES], non_blocking=True)
+        fuse(stage.view(torch.uint16), K, T)
+        tsdf.integrate(None, stage.view(torch.uint16), K, T, 1.0)
+        stats_host.copy_(stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for i in range(3):
+        step_local(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_local(3 * args.steps + i)
+    e1.record()
+    barrier()
+    local_ms = maxr_later = e0.elapsed_time(e1) / args.steps
+    tsdf_dims = [int(v) for v in tsdf._vol_dim]
 
     # ---- decode: 27 samples per active voxel, repeated to >= 10 M queries ----------------------
     vol.to_tensor()
@@ -297,8 +319,19 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         fps, dt = cpu_port(spec, frames, 2, 60)
+        # the CPU path BASELINE.json names: third_parties/fusion.py TSDFVolume CPU mode (oracle port), 206^3 @ 2.5 cm
+        from oracle.tsdf_oracle import TSDFOracle
+        from oracle import bnv_oracle as O
+        tv = TSDFOracle(np.stack([mn, mx], 1), 0.025)
+        d0, K0, T0 = frames[0]
+        dep = O.load_depth_u16(d0, spec.max_depth)[0].astype(np.float32)
+        t0 = time.perf_counter()
+        tv.integrate(np.zeros(d0.shape + (3,), np.float32), dep, K0, T0, 1.0)
+        t_tsdf = time.perf_counter() - t0
         cpu = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "2 steps of 60/480 image rows (x8 scaled) through oracle/bnv_oracle.py (numpy, float64 MLP)"}
+               "sample": "2 steps of 60/480 image rows (x8 scaled) through oracle/bnv_oracle.py (numpy, float64 MLP)",
+               "tsdf_cpu_frames_per_sec": 1.0 / t_tsdf,
+               "tsdf_sample": "1 frame, third_parties/fusion.py CPU-mode port (oracle/tsdf_oracle.py), %dx%dx%d voxels @ 2.5 cm" % tuple(tsdf_dims)}
     if rank == 0:
         out = {
             "metric": "fusion_frames_per_sec", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world,
@@ -312,6 +345,9 @@ def run_b200(args):
             "value_warm": 1e3 / warm_ms,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
                     "d2h_bytes_per_step": 32},
+            "local_scope": {"value": 1e3 / maxr(local_ms), "unit": "frames/s", "tsdf_dims": tsdf_dims,
+                            "what": "reference 'local' timer scope (run_e2e.py:250-252): neural fusion + coarse TSDF "
+                                    "integration at 2.5 cm, host depth in, frame stats out"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "encode (fused backproject + 8-corner MLP + scatter)", "bound": "tensor",
