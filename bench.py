@@ -38,6 +38,14 @@ N_FRAMES = 16
 WORKLOAD = "lounge"
 
 
+def traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), else None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,7 +266,7 @@ def run_b200(args):
     from bnv_fusion_b200.tsdf import TSDFVolume
     from bnv_fusion_b200.volume import get_world_range
     mn, mx, _ = get_world_range(spec.dimensions, 0.025)               # run_e2e.py:62-71: fixed 2.5 cm
-    tsdf = TSDFVolume(np.stack([mn, mx], 1), 0.025, device=dev)
+    tsdf = TSDFVolume(np.stack([mn, mx], 1), 0.025, device=dev, verbose=False)
     def step_local(i):
         _, K, T = frames[i % N_FRAMES]
         stage.copy_(host[i % N_FRAMES], non_blocking=True)
@@ -352,12 +360,16 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"kernel": "encode (fused backproject + 8-corner MLP + scatter)", "bound": "tensor",
                          "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                         "frac": enc_tflops / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
+                         "frac": enc_tflops / pk["tf_burst"],
+                         "traffic": traffic("encode_tc_kernel" if config.mlp_mode_name() == "tc16" else "encode_simt_kernel"),
+                         "peak_source": pk["src"],
                          "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "finalize_ms": float(np.mean(fin_ms))},
             "decode": {"value": n_q_job / (dec_ms_job * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_q_job,
                        "active_voxels_rank0": A, "ms": dec_ms_job,
                        "roofline": {"bound": "tensor", "achieved": dec_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                                    "frac": dec_tflops / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"]}},
+                                    "frac": dec_tflops / pk["tf_sustained"],
+                                    "traffic": traffic("decode_tc_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel"),
+                                    "peak_source": pk["src"]}},
             "cpu_baseline": cpu,
         }
         print(json.dumps(out))

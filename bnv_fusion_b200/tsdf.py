@@ -14,7 +14,7 @@ from . import _lib
 
 
 class TSDFVolume:
-    def __init__(self, vol_bnds, voxel_size, use_gpu=True, device="cuda:0"):
+    def __init__(self, vol_bnds, voxel_size, use_gpu=True, device="cuda:0", verbose=True):
         vol_bnds = np.asarray(vol_bnds, dtype=np.float64)
         assert vol_bnds.shape == (3, 2), "[!] `vol_bnds` should be of shape (3, 2)."
         self._lib = _lib.load()
@@ -33,7 +33,8 @@ class TSDFVolume:
         self._vol_bnds[:, 1] = self._vol_bnds[:, 0] + self._vol_dim * self._voxel_size
         self._vol_origin = self._vol_bnds[:, 0].astype(np.float32)
         self.gpu_mode = 1
-        print("Voxel volume size: {} x {} x {} - # points: {:,}".format(*self._vol_dim, int(np.prod(self._vol_dim))))
+        if verbose:
+            print("Voxel volume size: {} x {} x {} - # points: {:,}".format(*self._vol_dim, int(np.prod(self._vol_dim))))
 
     def __del__(self):
         try:
