@@ -129,7 +129,9 @@ __global__ void __launch_bounds__(kEncThreads) encode_simt_kernel(MapDev m, EncS
 }
 
 // mean of a scratch row (scatter_mean, local_point_fusion.py:125)
-__device__ __forceinline__ float scratch_mean(const MapDev& m, int32_t row, int j, int32_t cnt) {
+__device__ __forceinline__ float scratch_mean(const MapDev& m, int32_t row, int j, int32_t cnt, bool f32acc) {
+  if (f32acc)   // tensor-core mode: fp32 partial sums (add_row_f32)
+    return (float)((double)reinterpret_cast<const float*>(m.fsum + (size_t)row * kFeat)[j] / (double)cnt);
   const long long s = m.fsum[(size_t)row * kFeat + j];
   return (float)(((double)s / kFixScale) / (double)cnt);
 }
@@ -141,7 +143,7 @@ __device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new
 
 // finalize of the fused path: for every voxel touched this frame -> mean, count filter, running
 // average into the persistent map; clears the scratch.  8 lanes per voxel (one feature each).
-__global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, long long* __restrict__ stats,
+__global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, bool f32acc, long long* __restrict__ stats,
                                                              long long* __restrict__ user_stats,
                                                              float* __restrict__ user_navg) {
   const int n_touched = m.ctr[1];
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
     const int32_t row = m.touched[t];
     const int32_t key = m.fkeys[row];
     const int32_t cnt = m.fcnt[row];
-    const float mean = scratch_mean(m, row, lane8, cnt);
+    const float mean = scratch_mean(m, row, lane8, cnt, f32acc);
     m.fsum[(size_t)row * kFeat + lane8] = 0;
     if (cnt >= min_pts) {                                         // local_point_fusion.py:143-147
       int32_t slot = 0;
@@ -251,7 +253,7 @@ __global__ void sort_flag_kernel(MapDev m, int n, const int32_t* __restrict__ ro
 }
 
 __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ keys, const int32_t* __restrict__ rows,
-                                 const int32_t* __restrict__ flags, const int32_t* __restrict__ scan,
+                                 const int32_t* __restrict__ flags, const int32_t* __restrict__ scan, bool f32acc,
                                  int64_t out_cap, float* __restrict__ feats, int64_t* __restrict__ counts,
                                  int64_t* __restrict__ flat_ids, int64_t* __restrict__ coords) {
   const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -261,7 +263,7 @@ __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ ke
   const int32_t row = rows[t];
   const int32_t key = keys[t];
   const int32_t cnt = m.fcnt[row];
-  const float mean = scratch_mean(m, row, j, cnt);
+  const float mean = scratch_mean(m, row, j, cnt, f32acc);
   m.fsum[(size_t)row * kFeat + j] = 0;
   if (flags[t]) {
     const int64_t o = scan[t];
@@ -394,8 +396,8 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
   return BNV_OK;
 }
 
-static int launch_finalize(bnv_map_t* map, int min_pts, int64_t* frame_stats, float* navg, cudaStream_t s) {
-  finalize_fused_kernel<<<148 * 2, 256, 0, s>>>(map->d, min_pts, (long long*)map->stats, (long long*)frame_stats, navg);
+static int launch_finalize(bnv_map_t* map, int min_pts, int mode, int64_t* frame_stats, float* navg, cudaStream_t s) {
+  finalize_fused_kernel<<<148 * 8, 256, 0, s>>>(map->d, min_pts, mode == BNV_MLP_TC16, (long long*)map->stats, (long long*)frame_stats, navg);
   BNV_LAUNCH_CHECK("finalize_fused_kernel");
   return BNV_OK;
 }
@@ -435,7 +437,7 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   rc = launch_encode(map, src, true, (int64_t)H * W, enc, mode, s);
   if (rc) return rc;
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
-  rc = launch_finalize(map, min_pts, frame_stats, navg, s);
+  rc = launch_finalize(map, min_pts, mode, frame_stats, navg, s);
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[2], s));
   return rc;
 }
@@ -451,7 +453,7 @@ int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const b
   int rc = launch_encode(map, src, false, n_points, enc, mode, s);
   if (rc) return rc;
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
-  rc = launch_finalize(map, min_pts, frame_stats, navg, s);
+  rc = launch_finalize(map, min_pts, mode, frame_stats, navg, s);
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[2], s));
   return rc;
 }
@@ -492,7 +494,7 @@ int bnv_encode_points(bnv_map_t* map, const float* pts6, int64_t n_points, const
     BNV_CUDA(cub::DeviceScan::ExclusiveSum(map->cub_tmp, tmp, map->flags, map->scan, n, s));
     count_launch(2);
     sort_emit_kernel<<<(unsigned)(((int64_t)n * 8 + 255) / 256), 256, 0, s>>>(
-        map->d, n, map->sort_keys_out, map->sort_vals_out, map->flags, map->scan, out_capacity, feats, counts,
+        map->d, n, map->sort_keys_out, map->sort_vals_out, map->flags, map->scan, mode == BNV_MLP_TC16, out_capacity, feats, counts,
         flat_ids, coords);
     BNV_LAUNCH_CHECK("sort_emit_kernel");
   }

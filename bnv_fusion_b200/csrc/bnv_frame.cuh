@@ -107,6 +107,46 @@ __device__ __forceinline__ void add_row(const MapDev& m, int32_t slot, const flo
   for (int j = 0; j < kFeat; ++j) atomicAdd(s + j, (unsigned long long)__double2ll_rn((double)y[j] * kFixScale));
 }
 
+// tensor-core mode: fp32 partial sums in the first 32 bytes of the scratch row, accumulated with two
+// 16-byte vector reductions (red.global.add.v4.f32, sm_90+) + the count: 3 L2 operations per row instead
+// of 9.  The encode kernel is bound by the number of L2 atomic operations (tools/encode_experiment.py);
+// the features of this mode already carry fp16 operand rounding (1e-3), so fp32 summation-order noise
+// (1e-7) is immaterial.  The exact-parity CUDA-core mode keeps the order-independent fixed-point sums.
+__device__ __forceinline__ void add_row_f32(const MapDev& m, int32_t slot, const float (&y)[8]) {
+  float* s = reinterpret_cast<float*>(m.fsum + (size_t)slot * kFeat);
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(s), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(s + 4), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
+  atomicAdd(&m.fcnt[slot], 1);
+}
+
+// Warp-shuffle reduction per voxel before the L2 reductions: neighbouring pixels (lanes) mostly fall into
+// the same voxel, so runs of equal scratch rows are summed with a segmented inclusive scan (5 shuffle
+// steps) and only the last lane of a run issues the reductions, with the run length as the count.
+// Must be called by all 32 lanes; slot < 0 = nothing to add for this lane.
+__device__ __forceinline__ void add_row_f32_runs(const MapDev& m, int32_t slot, float (&y)[8]) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int32_t prev = __shfl_up_sync(full, slot, 1);
+  const unsigned heads = __ballot_sync(full, lane == 0 || prev != slot);
+  const int my_head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const bool take = lane - d >= my_head;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = __shfl_up_sync(full, y[j], d);
+      if (take) y[j] += v;
+    }
+  }
+  const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+  if (tail && slot >= 0) {
+    float* s = reinterpret_cast<float*>(m.fsum + (size_t)slot * kFeat);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(s), "f"(y[0]), "f"(y[1]), "f"(y[2]), "f"(y[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(s + 4), "f"(y[4]), "f"(y[5]), "f"(y[6]), "f"(y[7]) : "memory");
+    atomicAdd(&m.fcnt[slot], lane - my_head + 1);
+  }
+}
+
 __device__ __forceinline__ void scatter_row(const MapDev& m, int32_t flat, int32_t row, const float (&y)[8]) {
   const int32_t old = atomicCAS(&m.ftable[flat], kEmpty, row);
   const int32_t slot = old == kEmpty ? row : old;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
 template <bool FROM_DEPTH>
 __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc src, const uint8_t* __restrict__ gW,
                                                                 int w_bytes, int64_t n_threads,
-                                                                long long* __restrict__ stats) {
+                                                                long long* __restrict__ stats, int debug) {
   extern __shared__ __align__(128) uint8_t smem[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem);
   RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
       slot[k] = -1;
       if (inb && owns(g, ix, iy, iz)) {
-        slot[k] = claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
+        slot[k] = debug == 3 ? 0 : claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
         ++n_rows;
       }
     }
@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       // row = [x 1 | y 1 | z 1 | n0 n1 | n2 1 | 1 x 6]  (enc_perm: tcnn pads the 6 inputs to 16 with ones)
       const uint32_t in[8] = {pack_f16x2(xr[0], 1.f), pack_f16x2(xr[1], 1.f), pack_f16x2(xr[2], 1.f), nrm01, nrm2o, kOnes, kOnes, kOnes};
       float y[8];
+      if (debug == 1) { for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(in[j & 3]); } else
       chain_run<8, 8>(c, in, y);
-      if (slot[k] >= 0) add_row(m, slot[k], y);
+      if (debug == 5) add_row_f32_runs(m, slot[k], y); else
+      if (slot[k] >= 0 && debug < 2) add_row_f32(m, slot[k], y);
     }
     const unsigned mv = __ballot_sync(0xffffffffu, valid);
     const unsigned mi = __ballot_sync(0xffffffffu, inb);
@@ -339,18 +341,20 @@ int bnv_internal_mlp_forward_tc(const bnv_mlp_t* mlp, const float* x, int64_t n,
 int bnv_internal_encode_tc(bnv_map_t* map, const void* srcp, int from_depth, int64_t n_threads, const bnv_mlp_t* enc,
                            cudaStream_t s) {
   const EncSrc& src = *reinterpret_cast<const EncSrc*>(srcp);
+  const char* e = getenv("BNV_DEBUG_ENCODE");     // profiling experiments only
+  const int dbg = e ? atoi(e) : 0;
   const size_t smem = tc_smem_bytes(enc->in_pad);
   const int grid = tc_grid((n_threads + 127) / 128);
   if (from_depth) {
     int rc = set_smem(encode_tc_kernel<true>, smem);
     if (rc) return rc;
     encode_tc_kernel<true><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
-                                                        n_threads, (long long*)map->stats);
+                                                        n_threads, (long long*)map->stats, dbg);
   } else {
     int rc = set_smem(encode_tc_kernel<false>, smem);
     if (rc) return rc;
     encode_tc_kernel<false><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
-                                                         n_threads, (long long*)map->stats);
+                                                         n_threads, (long long*)map->stats, dbg);
   }
   BNV_LAUNCH_CHECK("encode_tc_kernel");
   return BNV_OK;

@@ -95,7 +95,9 @@ def test_tc_full_frame_paths_agree(model, dev):
             pts[None], vols[1].n_xyz, vols[1].min_coords, vols[1].max_coords, vols[1].voxel_size, return_dense=False)
         model._integrate(vols[1], coords, feats, counts)
     a, b = _map_sorted(vols[0]), _map_sorted(vols[1])
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    # same voxels and weights; features equal up to fp32 summation order (vector fp32 reductions)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    np.testing.assert_allclose(a[1], b[1], atol=2e-5, rtol=0)
     # fp32 CUDA-core mode on the same frames: same voxels, features within fp16 noise
     config.set_mlp_mode("fp32")
     v32 = _volume(spec, dev, pool_capacity=1 << 21)
