@@ -119,6 +119,8 @@ struct bnv_map {
   int64_t max_points;
   int64_t* stats;       // device int64[8] frame statistics accumulators
   void* dec_pack;       // [cap] x 16 B: fp16x8 copy of the exported features for the tensor-core decode gather
+  void* gtable;         // [(cap + 1) x 27] float: G[V][l] of the factored meshlize decode
+  size_t gtable_bytes;
   int timing;           // bnv_map_set_timing
   cudaEvent_t ev[3];    // before encode / after encode / after finalize
 };

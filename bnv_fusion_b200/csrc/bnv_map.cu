@@ -289,6 +289,8 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   alloc((void**)&m->bp_scan, (size_t)max_points * 4);
   alloc((void**)&m->stats, 8 * 8);
   alloc((void**)&m->dec_pack, (size_t)d.cap * 16);
+  m->gtable_bytes = ((size_t)d.cap + 1) * 27 * sizeof(float);
+  alloc((void**)&m->gtable, m->gtable_bytes);
   m->cub_tmp_bytes = (size_t)d.fcap * 16 + (1 << 20);
   alloc((void**)&m->cub_tmp, m->cub_tmp_bytes);
   if (e != cudaSuccess) {
@@ -315,7 +317,7 @@ int bnv_map_destroy(bnv_map_t* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.fcnt,
                   d.touched, d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
-                  m->sort_vals_out, m->flags, m->scan, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack,
+                  m->sort_vals_out, m->flags, m->scan, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);

@@ -287,6 +287,103 @@ __global__ void __launch_bounds__(NWG * 128, 1) decode_tc_kernel(MapDev m, DecAr
   tc_teardown<4>(S.sh);
 }
 
+// ---- factored decode of the meshlize sample blocks ------------------------------------------------------
+// SparseVolume.meshlize samples id + {-0.5, 0, 0.5}^3 around every active voxel (sparse_volume.py:717-731),
+// so every (query, corner) row of decode_pts is MLP(l, feat_V) with V a voxel and l in {-0.5, 0, 0.5}^3:
+// only 27 distinct rows per voxel exist, each shared by up to 8 queries of neighbouring voxels.  The
+// factored path evaluates G[V][l] once on the tensor cores (27 rows per exported voxel + one "miss" voxel
+// with zero features, rule D7) and then blends per sample with the reference's op order (D2-D6).  Same MLP
+// rows, same blend => bit-identical to decode_tc_kernel on the same coordinates, with 8x fewer MLP rows.
+__global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __restrict__ packed, int64_t n_rows,
+                                                                const uint8_t* __restrict__ gW, int w_bytes,
+                                                                float* __restrict__ G) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  TcSmem& S = *reinterpret_cast<TcSmem*>(smem);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
+  const int64_t total = (n_rows + 1) * 27;                       // voxel n_rows = the miss voxel
+  const int64_t n_tiles = (total + 127) / 128;
+  uint32_t w_ls[3], w_c1[3];                                     // l = -0.5, 0, +0.5
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float l = 0.5f * (float)(d - 1);
+    float sn, cs;
+    __sincosf(l, &sn, &cs);
+    w_ls[d] = pack_f16x2(l, sn);
+    w_c1[d] = pack_f16x2(cs, 1.0f);
+  }
+  for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
+    const int64_t row = tile * 128 + r;
+    const int64_t v = row / 27;
+    const int li = (int)(row - v * 27);
+    uint4 f = make_uint4(0, 0, 0, 0);
+    if (row < total && v < n_rows) f = __ldg(packed + v);
+    const int dx = li / 9, dy = (li / 3) % 3, dz = li % 3;
+    const uint32_t in[16] = {f.x, f.y, f.z, f.w, w_ls[dx], w_c1[dx], w_ls[dy], w_c1[dy], w_ls[dz], w_c1[dz],
+                             kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+    float y[1];
+    chain_run<16, 1>(c, in, y);
+    if (row < total) G[row] = y[0];
+  }
+  tc_teardown<kNWG>(S.sh);
+}
+
+// per sample: 8 corner lookups into G + trilinear blend + mask + prior (rules D1-D6)
+__global__ void __launch_bounds__(256) blend_blocks_kernel(MapDev m, DecArgs a, const float* __restrict__ G) {
+  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (q >= a.n_queries) return;
+  const GeomDev& g = m.g;
+  const int64_t v = a.first_voxel + q / 27;
+  const int s = (int)(q % 27);
+  const int32_t flat0 = m.keys[v];
+  const int id[3] = {flat0 / g.nyz, (flat0 % g.nyz) / g.n[2], flat0 % g.n[2]};
+  const int o[3] = {s / 9 - 1, (s / 3) % 3 - 1, s % 3 - 1};     // sample offset / 0.5
+  // per axis, floor (j = 0) and ceil (j = 1) corner: voxel index, l digit (0: -0.5, 1: 0, 2: +0.5), 1 - |l|
+  int nbv[3][2], ld[3][2];
+  float tt[3][2], nbf[3][2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    nbv[d][0] = o[d] < 0 ? id[d] - 1 : id[d];
+    nbv[d][1] = o[d] > 0 ? id[d] + 1 : id[d];
+    ld[d][0] = o[d] == 0 ? 1 : 2;
+    ld[d][1] = o[d] == 0 ? 1 : 0;
+    tt[d][0] = tt[d][1] = o[d] == 0 ? 1.0f : 0.5f;
+    nbf[d][0] = (float)nbv[d][0];
+    nbf[d][1] = (float)nbv[d][1];
+  }
+  constexpr int SX[8] = {0, 1, 0, 0, 1, 1, 0, 1}, SY[8] = {0, 0, 1, 0, 1, 0, 1, 1}, SZ[8] = {0, 0, 0, 1, 0, 1, 1, 1};
+  float wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = __fmul_rn(__fmul_rn(tt[0][SX[k]], tt[1][SY[k]]), tt[2][SZ[k]]);
+    wsum = k == 0 ? w : __fadd_rn(wsum, w);
+  }
+  float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ix = nbv[0][SX[k]], iy = nbv[1][SY[k]], iz = nbv[2][SZ[k]];
+    int64_t gv = a.n_rows;                                        // miss voxel
+    float wt = 0.f;
+    if (ix >= 0 && iy >= 0 && iz >= 0 && ix < g.n[0] && iy < g.n[1] && iz < g.n[2]) {
+      const int32_t slot = __ldg(m.table + ((int64_t)ix * g.nyz + iy * g.n[2] + iz));
+      if (slot >= 0 && slot < a.n_rows) {
+        gv = slot;
+        wt = __ldg(a.weights_rows + slot);
+      }
+    }
+    minw = fminf(minw, wt);
+    const float y = __ldg(G + gv * 27 + (ld[0][SX[k]] * 9 + ld[1][SY[k]] * 3 + ld[2][SZ[k]]));
+    const float wn = __fdiv_rn(__fmul_rn(__fmul_rn(tt[0][SX[k]], tt[1][SY[k]]), tt[2][SZ[k]]), wsum);
+    sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y, g.vs), wn));
+    if (a.tsdf) {
+      const float nb[3] = {nbf[0][SX[k]], nbf[1][SY[k]], nbf[2][SZ[k]]};
+      dsum = __fadd_rn(dsum, __fmul_rn(tsdf_nearest(a, g, nb), wn));
+    }
+  }
+  bool mask;
+  a.out_sdf[q] = finish_blend(sdf, dsum, minw, a, g.vs, &mask);
+}
+
 }  // namespace tc
 }  // namespace bnv
 
@@ -366,6 +463,22 @@ int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_
   if (a.n_rows > 0) {
     pack_rows_kernel<<<(unsigned)((a.n_rows + 255) / 256), 256, 0, s>>>(a.feats_rows, a.n_rows, (uint4*)map->dec_pack);
     BNV_LAUNCH_CHECK("pack_rows_kernel");
+  }
+  if (a.voxel_blocks && !getenv("BNV_DECODE_DIRECT")) {
+    // factored meshlize decode: G table on the tensor cores, then the per-sample blend
+    if ((size_t)(a.n_rows + 1) * 27 * sizeof(float) > map->gtable_bytes) {
+      set_error("decode: G table of %lld rows exceeds the map's capacity", (long long)a.n_rows);
+      return BNV_E_CAPACITY;
+    }
+    int rc = set_smem(gtable_tc_kernel, smem);
+    if (rc) return rc;
+    const int64_t tiles = ((a.n_rows + 1) * 27 + 127) / 128;
+    gtable_tc_kernel<<<tc_grid(tiles), kThreads, smem, s>>>((const uint4*)map->dec_pack, a.n_rows, (const uint8_t*)dec->w16,
+                                                            (int)dec->w16_bytes, (float*)map->gtable);
+    BNV_LAUNCH_CHECK("gtable_tc_kernel");
+    blend_blocks_kernel<<<(unsigned)((a.n_queries + 255) / 256), 256, 0, s>>>(map->d, a, (const float*)map->gtable);
+    BNV_LAUNCH_CHECK("blend_blocks_kernel");
+    return BNV_OK;
   }
   const char* e = getenv("BNV_TC_NWG");      // profiling experiments only
   const int nwg = e ? atoi(e) : 4;

@@ -113,6 +113,15 @@ def test_tc_full_frame_paths_agree(model, dev):
     coords, _, _, _ = vol.to_tensor()
     vol.weights += 8.0
     tc = vol.decode_voxel_blocks(model.nerf)
+    # the factored block decode (G table + blend) is bit-identical to the generic per-query kernel
+    prior = (torch.randn(1, 1, 31, 33, 35, device=dev) * 0.004)
+    tcp = vol.decode_voxel_blocks(model.nerf, prior)
+    n_chk = 20000
+    q = torch.from_numpy(O.meshlize_samples(coords[:n_chk].cpu().numpy())).to(dev)[None]
+    assert torch.equal(vol.decode_pts(q, model.nerf, None, is_coords=True)[0, :, :, 0], tc[:n_chk].reshape(n_chk, 27))
+    assert torch.equal(vol.decode_pts(q, model.nerf, prior, is_coords=True)[0, :, :, 0], tcp[:n_chk].reshape(n_chk, 27))
+    part = vol.decode_voxel_blocks(model.nerf, prior, first=1234, count=777)
+    assert torch.equal(part, tcp[1234:1234 + 777])
     config.set_mlp_mode("fp32")
     ref = vol.decode_voxel_blocks(model.nerf)
     config.set_mlp_mode("tc16")
