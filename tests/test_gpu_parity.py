@@ -323,3 +323,27 @@ def test_full_frame_paths_agree_and_properties(model, dev):
     far = torch.full((1, 10, 1, 3), 3.25, device=dev)
     out, mask = vol.decode_pts(far, model.nerf, None, is_coords=True, return_mask=True)
     assert not mask.any() and torch.all(out == np.float32(0.01))
+
+
+def test_count_optim_and_query_tensor(model, dev):
+    """SparseVolume.count_optim (sparse_volume.py:602-622): weights[rows(keys)] += 1 once per distinct row."""
+    spec = synth.stream_spec("parity64")
+    vol = _volume(spec, dev, pool_capacity=1 << 16)
+    for fi in range(3):
+        d, K, T = synth.make_frame(spec, fi, seed=0)
+        model.fuse_depth_frame(vol, _depth_to_dev(d, dev), K, T, spec.max_depth)
+    coords, feats, weights, hits = vol.to_tensor()
+    w0 = weights.clone()
+    n = coords.shape[0]
+    # keys shaped like decode_pts' neighbour tensor [1, 8, B, S, 3]; rows 0..99 three times, plus misses
+    sel = torch.arange(100, device=dev)
+    keys = torch.cat([coords[sel], coords[sel], coords[sel], torch.full((40, 3), 31, device=dev)]).float()
+    keys = keys.reshape(1, 1, -1, 1, 3)
+    vol.count_optim(keys)
+    expect = w0.clone()
+    expect[sel] += 1                                            # non-accumulating for duplicates
+    hit31 = ((coords == 31).all(1)).nonzero().flatten()
+    expect[hit31] += 1
+    assert torch.equal(vol.weights, expect)
+    f, w, h = vol._query_tensor(coords[:50].reshape(1, 50, 1, 3))
+    assert torch.equal(w.reshape(-1), vol.weights[:50, 0]) and torch.equal(f.reshape(-1, 8), feats[:50])
