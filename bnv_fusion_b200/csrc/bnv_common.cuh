@@ -128,7 +128,8 @@ struct bnv_map {
 struct bnv_mlp {
   int n_in, n_out, in_pad, out_pad, device;
   int64_t n_params;
-  float* w32;           // device fp32 copy of params (row-major [out,in] blocks, as given)
+  float* w32;           // device fp32 k-major image for the CUDA-core kernels (bnv_mlp_simt.cuh)
+  float* wraw;          // device fp32 copy of params as given (row-major [out,in] blocks): backward pass
   void* w16;            // device fp16 image in the UMMA canonical shared-memory layout
   size_t w16_bytes;
 };

@@ -100,6 +100,12 @@ int bnv_mlp_create(bnv_mlp_t** out, const float* params, int64_t n_params, int n
     bnv_mlp_destroy(m);
     return cuda_fail(e, "bnv_mlp_create upload");
   }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->wraw, n_params * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(m->wraw, params, n_params * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    bnv_mlp_destroy(m);
+    return cuda_fail(e, "bnv_mlp_create upload (raw)");
+  }
   int rc = bnv_internal_pack_tc_weights(m, params);
   if (rc != BNV_OK) {
     bnv_mlp_destroy(m);
@@ -113,6 +119,7 @@ int bnv_mlp_destroy(bnv_mlp_t* m) {
   if (!m) return BNV_OK;
   cudaSetDevice(m->device);
   if (m->w32) cudaFree(m->w32);
+  if (m->wraw) cudaFree(m->wraw);
   if (m->w16) cudaFree(m->w16);
   delete m;
   return BNV_OK;

@@ -36,6 +36,35 @@ def geometry_key(n_xyz, bound_min, voxel_size):
     return n + b + (float(voxel_size),)
 
 
+class _DecodeFn(torch.autograd.Function):
+    """decode_pts as a differentiable function of the exported features (forward: the fused decode kernel
+    in the configured precision; backward: bnv_decode_sdf_backward, fp32)."""
+
+    @staticmethod
+    def forward(ctx, feats, vol, q, weights, nerf, tsdf, dims, is_coords):
+        f = feats.detach().contiguous()
+        out = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+        _lib.check(vol._lib.bnv_decode_sdf(vol._handle, _lib.ptr(q), q.shape[0], 1 if is_coords else 0, _lib.ptr(f),
+                                           _lib.ptr(weights), f.shape[0], nerf._mlp_handle(), int(vol.min_pts_in_grid),
+                                           config.mlp_mode(), _lib.ptr(tsdf), dims, _lib.ptr(out), None, vol._stream()),
+                   "bnv_decode_sdf")
+        ctx.vol, ctx.nerf, ctx.is_coords = vol, nerf, is_coords
+        ctx.save_for_backward(f, q, weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        f, q, weights = ctx.saved_tensors
+        vol = ctx.vol
+        g = grad_out.detach().reshape(-1).float().contiguous()
+        grad = torch.zeros_like(f)
+        _lib.check(vol._lib.bnv_decode_sdf_backward(vol._handle, _lib.ptr(q), q.shape[0], 1 if ctx.is_coords else 0,
+                                                    _lib.ptr(f), _lib.ptr(weights), f.shape[0], ctx.nerf._mlp_handle(),
+                                                    int(vol.min_pts_in_grid), _lib.ptr(g), _lib.ptr(grad), vol._stream()),
+                   "bnv_decode_sdf_backward")
+        return grad, None, None, None, None, None, None, None
+
+
 class SparseVolume:
     def __init__(self, n_feats, voxel_size, dimensions, min_pts_in_grid, capacity=100000,
                  device="cuda:0", max_points=None, pool_capacity=None):
@@ -226,9 +255,6 @@ class SparseVolume:
             feats, weights = self.features, self.weights
         else:
             _, feats, weights, _ = self._export_tmp()
-        if torch.is_grad_enabled() and getattr(feats, "requires_grad", False):
-            raise NotImplementedError("decoder backward (global optimisation) is a later row of the "
-                                      "scope table (SURVEY.md §8f rank 2)")
         feats = feats.detach().contiguous()
         weights = weights.detach().reshape(-1).contiguous()
         tsdf, dims = None, None
@@ -258,6 +284,11 @@ class SparseVolume:
         assert shp[-1] == 3
         q = coords.detach().reshape(-1, 3).float().contiguous()
         nq = q.shape[0]
+        leaf = self.features if query_tensor else None
+        if leaf is not None and torch.is_grad_enabled() and leaf.requires_grad and not return_mask:
+            # NeuralMap.optimize (run_e2e.py:111-156): gradients flow to volume.features only
+            out = _DecodeFn.apply(leaf, self, q, weights, nerf, tsdf, dims, bool(is_coords))
+            return out.reshape(shp[:-1] + [1])
         out = torch.empty(nq, dtype=torch.float32, device=self.device)
         mask = torch.empty(nq, dtype=torch.uint8, device=self.device) if return_mask else None
         _lib.check(self._lib.bnv_decode_sdf(self._handle, _lib.ptr(q), nq, 1 if is_coords else 0,

@@ -176,6 +176,15 @@ int bnv_decode_sdf(bnv_map_t* map, const float* coords_dev, int64_t n_queries, i
                    const bnv_mlp_t* dec, int min_pts, int mode, const float* tsdf_delta_dev,
                    const int32_t* tsdf_dims_host, float* out_sdf_dev, uint8_t* out_mask_dev,
                    void* stream);
+/* Backward of bnv_decode_sdf w.r.t. the exported features -- what torch autograd computes through
+ * SparseVolume.decode_pts in NeuralMap.optimize (src/run_e2e.py:111-156, volume.features is the only leaf):
+ * grad_feats_rows_dev [n_rows, F] += d(sum_q grad_out[q] * sdf[q]) / d(feats_rows).  The caller zero-fills
+ * grad_feats_rows_dev.  fp32 CUDA cores. */
+int bnv_decode_sdf_backward(bnv_map_t* map, const float* coords_dev, int64_t n_queries, int is_coords,
+                            const float* feats_rows_dev, const float* weights_rows_dev, int64_t n_rows,
+                            const bnv_mlp_t* dec, int min_pts, const float* grad_out_dev,
+                            float* grad_feats_rows_dev, void* stream);
+
 /* The sampling half of SparseVolume.meshlize (sparse_volume.py:697-738) fused with the decode:
  * for active voxels [first, first+count) evaluate the 27 samples id + {-0.5,0,0.5}^3.
  * out_sdf_dev [count,27] ('ij' meshgrid order). */

@@ -422,3 +422,49 @@ def backproject(depth, mask, K, T_wc):
     nw = (n[:, 0:1] * T[None, :3, 0] + n[:, 1:2] * T[None, :3, 1]) + n[:, 2:3] * T[None, :3, 2]
     out = np.concatenate([pw, nw], axis=-1)[np.asarray(mask).reshape(-1)]
     return out.astype(F32)
+
+
+# --------------------------------------------------------------------------- #
+# decode backward (global optimisation)
+# --------------------------------------------------------------------------- #
+def decode_pts_backward(vmap, coords, dec_params, grad_out, min_pts=8, is_coords=True, div_mode="recip"):
+    """d(sum(grad_out * sdf)) / d(features) for SparseVolume.decode_pts (sparse_volume.py:768-833) as
+    autograd computes it in NeuralMap.optimize (src/run_e2e.py:111-156; the features are the only leaf).
+    Returns {flat_id: grad[8]} (float64 accumulation).  The TSDF prior and the `voxel_size` fallback of
+    masked queries do not depend on the features."""
+    grid = vmap.grid
+    c = np.asarray(coords, F32).reshape(-1, 3)
+    if not is_coords:
+        c = _scalar_div((c - grid.bmin[None]).astype(F32), grid.voxel_size, div_mode)
+    g_out = np.asarray(grad_out, np.float64).reshape(-1)
+    nbr = get_neighbors(c)
+    l = (c[None] - nbr).astype(F32)
+    w = np.prod((F32(1) - np.abs(l)).astype(F32), axis=-1).astype(np.float64)
+    ijk = nbr.astype(np.int64)
+    inside = np.all((ijk >= 0) & (ijk < np.asarray(grid.n_xyz)[None, None]), axis=-1)
+    flat = flatten_i32(np.where(inside[..., None], ijk, 0), grid.n_xyz)
+    f, wt, _, found = vmap.query(flat.reshape(-1))
+    found = found.reshape(8, -1) & inside
+    f = np.where(found.reshape(-1)[:, None], f, F32(0))
+    wt = np.where(found, wt.reshape(8, -1), F32(0))
+    mask = wt.min(axis=0) >= F32(min_pts)
+    wn = w / w.sum(axis=0, keepdims=True)
+    x = np.concatenate([positional_encoding(l).reshape(-1, 9), f], axis=-1).astype(np.float64)
+    blocks = [b.astype(np.float64) for b in mlp_blocks(dec_params, 17, 1)]
+    X = np.ones((x.shape[0], 32))
+    X[:, :17] = x
+    h1 = X @ blocks[0].T
+    h2 = np.maximum(h1, 0) @ blocks[1].T
+    h3 = np.maximum(h2, 0) @ blocks[2].T
+    dy = (g_out[None] * wn * grid.voxel_size * mask[None]).reshape(-1)          # d loss / d y_k
+    d3 = (dy[:, None] * blocks[3][0][None]) * (h3 > 0)
+    d2 = (d3 @ blocks[2]) * (h2 > 0)
+    d1 = (d2 @ blocks[1]) * (h1 > 0)
+    dfeat = (d1 @ blocks[0])[:, 9:17]
+    out = {}
+    fl = flat.reshape(-1)
+    fd = found.reshape(-1)
+    for i in np.nonzero(fd & (dy != 0))[0]:
+        k = int(fl[i])
+        out[k] = out.get(k, 0) + dfeat[i]
+    return out

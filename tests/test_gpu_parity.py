@@ -347,3 +347,49 @@ def test_count_optim_and_query_tensor(model, dev):
     assert torch.equal(vol.weights, expect)
     f, w, h = vol._query_tensor(coords[:50].reshape(1, 50, 1, 3))
     assert torch.equal(w.reshape(-1), vol.weights[:50, 0]) and torch.equal(f.reshape(-1, 8), feats[:50])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc16"])
+def test_decode_backward_vs_reference_autograd(model, golden_dir, dev, mode):
+    """d decode_pts / d volume.features (NeuralMap.optimize) vs the gradients the reference's own code +
+    torch autograd produce (tests/golden/make_golden_grad.py)."""
+    from bnv_fusion_b200 import config
+    config.set_mlp_mode(mode)
+    g = np.load(os.path.join(golden_dir, "golden_parity64.npz"))
+    gg = np.load(os.path.join(golden_dir, "golden_decode_grad.npz"))
+    spec = synth.stream_spec("parity64")
+    vol = _volume(spec, dev, pool_capacity=1 << 16)
+    vol.insert(torch.from_numpy(g["recip/map_coords"]).to(dev), torch.from_numpy(g["recip/map_feats"]).to(dev),
+               torch.from_numpy(g["recip/map_weights"]).to(dev), torch.from_numpy(g["recip/map_hits"]).to(dev))
+    coords, _, _, _ = vol.to_tensor()
+    n = vol._n_xyz_host
+    flat = (coords[:, 0] * n[1] * n[2] + coords[:, 1] * n[2] + coords[:, 2]).cpu().numpy()
+    ref_flat = O.flatten_i32(gg["coords"], n)
+    perm = np.array([dict(zip(ref_flat.tolist(), range(len(ref_flat))))[int(k)] for k in flat])
+    vol.features = torch.nn.Parameter(vol.features)
+    prior = torch.from_numpy(g["recip/tsdf_delta"]).to(dev)[None, None]
+    for name in ("mesh", "rand"):
+        q = torch.from_numpy(gg[f"{name}_q"]).to(dev)[None]
+        r = torch.from_numpy(gg[f"{name}_r"]).to(dev)
+        sdf = vol.decode_pts(q, model.nerf, prior, is_coords=True)
+        assert sdf.requires_grad
+        np.testing.assert_allclose(sdf.detach()[0, :, :, 0].cpu().numpy(), gg[f"{name}_sdf"], atol=1e-4 if mode == "tc16" else 2e-6, rtol=0)
+        vol.features.grad = None
+        (sdf[0, :, :, 0] * r).sum().backward()
+        grad = vol.features.grad.cpu().numpy()
+        ref = gg[f"{name}_grad"][perm]
+        assert np.abs(ref).max() > 1e-4
+        np.testing.assert_allclose(grad, ref, atol=3e-7, rtol=2e-4)
+    # one Adam step through the public objects, as NeuralMap.optimize does, then write back
+    opt = torch.optim.Adam([vol.features], lr=0.001)
+    before = vol.features.detach().clone()
+    opt.zero_grad()
+    q = torch.from_numpy(gg["mesh_q"]).to(dev)[None]
+    loss = vol.decode_pts(q, model.nerf, prior, is_coords=True).abs().mean()
+    loss.backward()
+    opt.step()
+    assert float((vol.features.detach() - before).abs().max()) > 0
+    vol.insert(vol.active_coordinates, vol.features, vol.weights, vol.num_hits)
+    f2, _, _ = vol.query(vol.active_coordinates)
+    assert torch.equal(f2, vol.features.detach())
+    config.set_mlp_mode("fp32")

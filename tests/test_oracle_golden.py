@@ -155,3 +155,22 @@ def test_recip_vs_true_differ_rarely():
     b = np.floor(O._scalar_div(x, 0.01, "true"))
     frac = (a != b).mean()
     assert 0 < frac < 1e-4
+
+
+def test_decode_backward_oracle(golden_dir, tcnn_params):
+    """Gradient of decode_pts w.r.t. the voxel features vs the reference's own autograd."""
+    g = _load(golden_dir, "golden_parity64.npz")
+    gg = _load(golden_dir, "golden_decode_grad.npz")
+    spec = synth.stream_spec("parity64")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vm = O.VoxelMap(grid)
+    vm.insert(O.flatten_i32(g["recip/map_coords"], grid.n_xyz), g["recip/map_feats"], g["recip/map_weights"][:, 0],
+              g["recip/map_hits"][:, 0])
+    pos = {int(k): i for i, k in enumerate(O.flatten_i32(gg["coords"], grid.n_xyz))}
+    for name in ("mesh", "rand"):
+        gr = O.decode_pts_backward(vm, gg[f"{name}_q"].reshape(-1, 3), tcnn_params["decoder"], gg[f"{name}_r"].reshape(-1), 8, True)
+        mine = np.zeros(gg[f"{name}_grad"].shape)
+        for k, v in gr.items():
+            mine[pos[k]] = v
+        assert np.abs(gg[f"{name}_grad"]).max() > 1e-4
+        np.testing.assert_allclose(mine, gg[f"{name}_grad"], atol=2e-8, rtol=0)
