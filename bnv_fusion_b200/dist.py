@@ -93,7 +93,7 @@ def select_needed(flat, n_xyz, rank, world, brick_log2):
 class TileShardedFusion:
     """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
 
-    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 17, group=None):
+    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None):
         import torch
         from . import _lib
         self.torch, self._lib = torch, _lib
