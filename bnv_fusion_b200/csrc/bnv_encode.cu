@@ -213,7 +213,15 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
       m.fcnt[row] = 0;
     }
   }
-  if (integrated) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 3), (unsigned long long)integrated);
+  // one statistics atomic per block (same-address atomics serialise in L2)
+  __shared__ int s_integrated;
+  if (threadIdx.x == 0) s_integrated = 0;
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) integrated += __shfl_xor_sync(0xffffffffu, integrated, o);
+  if ((threadIdx.x & 31) == 0 && integrated) atomicAdd(&s_integrated, integrated);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_integrated) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 3), (unsigned long long)s_integrated);
   // last block publishes the frame statistics and re-arms the counters
   __shared__ bool last;
   __threadfence();

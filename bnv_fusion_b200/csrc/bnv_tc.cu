@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const GeomDev& g = m.g;
   const int64_t n_tiles = (n_threads + 127) / 128;
+  int st_valid = 0, st_inb = 0, st_rows = 0;           // frame statistics, flushed once per warp at the end
   for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
     const int64_t idx = tile * 128 + r;
     float p[6];
@@ -149,16 +150,20 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       if (debug == 5) add_row_f32_runs(m, slot[k], y); else
       if (slot[k] >= 0 && debug < 2) add_row_f32(m, slot[k], y);
     }
-    const unsigned mv = __ballot_sync(0xffffffffu, valid);
-    const unsigned mi = __ballot_sync(0xffffffffu, inb);
-    int rr = n_rows;
+    st_valid += valid ? 1 : 0;
+    st_inb += inb ? 1 : 0;
+    st_rows += n_rows;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
-    if ((threadIdx.x & 31) == 0 && (mv | mi)) {
-      atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)__popc(mv));
-      atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)rr);
-      atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)__popc(mi));
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
+    st_inb += __shfl_xor_sync(0xffffffffu, st_inb, o);
+    st_rows += __shfl_xor_sync(0xffffffffu, st_rows, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (st_valid | st_inb)) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)st_valid);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)st_rows);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)st_inb);
   }
   tc_teardown<kNWG>(S.sh);
 }

@@ -95,6 +95,46 @@ __global__ void k_ldst(int reps, int mode, long long* out) {
   if (threadIdx.x < 32) tmem_dealloc(sh.tmem, 512);
 }
 
+// fp16 accumulators: where do the 16-bit D elements live in TMEM?  A = ones [128 x 16], B[n][k] = (k == 0) * (n + 1) / 64
+// => D[m][n] = (n + 1) / 64.  Dump lane 0: raw 32-bit columns 0..63, and the .pack::16b view of the same columns.
+__global__ void k_probe_f16acc(uint32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Sh& sh = *reinterpret_cast<Sh*>(smem);
+  __half* w = reinterpret_cast<__half*>(smem + 1024);
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) w[i] = __float2half(0.f);
+  __syncthreads();
+  if (threadIdx.x < 64) {            // canonical K-major no-swizzle: byte(n,k) = (k/8)*LBO + (n/8)*128 + (n%8)*16 + (k%8)*2, LBO = 1024
+    const int n = threadIdx.x;
+    w[((0 / 8) * 1024 + (n / 8) * 128 + (n % 8) * 16) / 2] = __float2half((n + 1) / 64.f);
+  }
+  if (threadIdx.x == 0) { mbar_init(&sh.bar[0], 1); mbar_fence_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&sh.tmem, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t tl = sh.tmem + ((uint32_t)(warp * 32) << 16);
+  uint32_t ones[8];
+  for (int i = 0; i < 8; ++i) ones[i] = 0x3C003C00u;
+  uint32_t junk[32];
+  for (int i = 0; i < 32; ++i) junk[i] = 0xDEAD0000u + i;
+  tmem_st32(tl, junk); tmem_st32(tl + 32, junk);
+  tmem_st8(tl + 448, ones);
+  tmem_wait_st(); tc_fence_before(); __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    umma_ts_f16(sh.tmem, sh.tmem + 448, smem_desc_kmajor(smem_u32(w), 1024, 128), idesc_f16_m128(64, false), 0u);
+    umma_commit(&sh.bar[0]);
+  }
+  mbar_wait(&sh.bar[0], 0);
+  tc_fence_after();
+  uint32_t a[32], b[32], p[32];
+  tmem_ld32(tl, a); tmem_ld32(tl + 32, b); tmem_wait_ld();
+  tmem_ld32_pack16(tl, p); tmem_wait_ld();
+  if (threadIdx.x == 0) for (int i = 0; i < 32; ++i) { out[i] = a[i]; out[32 + i] = b[i]; out[64 + i] = p[i]; }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(sh.tmem, 512);
+}
+
 template <int N> void run_mma(long long* d, long long* h) {
   cudaFuncSetAttribute(k_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
   for (int iss : {1, 4}) {
@@ -122,6 +162,20 @@ int main() {
       long long mx = 0; for (int w = 0; w < warps; ++w) mx = h[w] > mx ? h[w] : mx;
       printf("%s warps=%2d : %.1f cyc/iter (slowest warp)\n", mode == 0 ? "LDTM.x32+wait      " : mode == 1 ? "STTM.x32+wait      " : "ld64+cvt32+st32    ", warps, (double)mx / 200);
     }
+  {
+    uint32_t *dp, hp[96];
+    cudaMalloc(&dp, 96 * 4);
+    cudaFuncSetAttribute(k_probe_f16acc, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+    k_probe_f16acc<<<1, 128, 40000>>>(dp);
+    cudaMemcpy(hp, dp, 96 * 4, cudaMemcpyDeviceToHost);
+    printf("fp16-accumulator probe, lane 0 (expect D[n] = (n+1)/64 as fp16: 0x2400 0x2800 0x2A00 0x2C00 ...)\n raw cols 0..15 :");
+    for (int i = 0; i < 16; ++i) printf(" %08x", hp[i]);
+    printf("\n raw cols 32..39:");
+    for (int i = 32; i < 40; ++i) printf(" %08x", hp[i]);
+    printf("\n pack::16b 0..15:");
+    for (int i = 64; i < 80; ++i) printf(" %08x", hp[i]);
+    printf("\n");
+  }
   cudaError_t e = cudaDeviceSynchronize();
   printf("status: %s\n", cudaGetErrorString(e));
   return 0;
