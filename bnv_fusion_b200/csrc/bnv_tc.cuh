@@ -8,9 +8,9 @@
 //
 // Row r of a tile is TMEM lane r and is owned by thread r of a 128-thread "row warpgroup", so the
 // activations need no shared-memory round trip and no swizzled layouts; only the weights (B, K-major,
-// no swizzle) sit in shared memory, loaded once per persistent CTA.  Thread 0 of each row warpgroup
-// issues that warpgroup's UMMAs; several warpgroups (one TMEM slot each) keep the tensor pipe busy
-// while the others run their epilogues.
+// no swizzle) sit in shared memory, loaded once per persistent CTA.  One elected lane of one warp of
+// each row warpgroup issues that warpgroup's UMMAs; four warpgroups (one 128-column TMEM slot each) keep
+// the tensor pipe busy while the others run their epilogues.  See "The software-pipelined chain" below.
 #pragma once
 #include <cuda_fp16.h>
 
@@ -20,7 +20,7 @@ namespace bnv {
 namespace tc {
 
 constexpr int kRowsPerTile = 128;
-constexpr int kSlotCols = 128;       // TMEM columns per in-flight tile: D [0,64) fp32, A [64,96) packed fp16
+constexpr int kSlotCols = 128;       // TMEM columns per chain (layout below)
 constexpr int kACol = 64;
 
 // ---- shared-memory weight image (built on the host, bnv_tc.cu) ---------------------------------
@@ -212,51 +212,148 @@ __device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t lo_bits, uint32_t h
   return r;
 }
 
-// ---- per-thread view of one TMEM slot ------------------------------------------------------------------
-// Each 128-thread row warpgroup owns one TMEM slot and one mbarrier.  After the warpgroup has stored
-// the A operand of the next layer (tcgen05.st + wait + named barrier), its thread 0 issues that
-// layer's UMMAs itself and commits them to the warpgroup's mbarrier; the tensor pipe interleaves the
-// UMMAs of the different warpgroups, so no dedicated MMA warp (and no polling) is needed.
-struct RowChain {
-  uint32_t t_d;        // TMEM address of this warp's lanes, column 0 of the slot (D)
-  uint32_t t_a;        // ... column kACol of the slot (A)
-  uint32_t d_slot;     // slot base (lane 0), for the issuing thread
-  uint64_t* bar_d;     // "D of the last issued layer is complete" (tcgen05.commit, count 1)
-  uint32_t par_d;      // phase parity of bar_d this thread waits for next
-  uint32_t w_saddr;    // shared-memory address of the weight image
-  const uint8_t* w_gen; // same, generic pointer (fp32 W3 for the CUDA-core output layer)
-  int bar_id;          // named barrier of this warpgroup (1 + warpgroup index)
-  bool issuer;         // the warpgroup's UMMA-issuing thread (lane 0 of warp wg % 4)
-};
-
 __device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
 
-// All rows of the tile have their A operand in TMEM -> run layer L (compile-time K, N) on the tensor core
-template <int K, int N>
-__device__ __forceinline__ void chain_issue_layer(RowChain& c, int w_off) {
+// =================================================================================================
+// The software-pipelined chain.  Per item (one 128-row tile through the 4-layer MLP):
+//
+//   L0 -> epi -> L1 -> [shadow] -> epi -> L2 -> epi -> { L3 (N = 16) + L0 of the NEXT item, one issue burst }
+//
+// The output layer also runs on the tensor core (h3 rounded to fp16 like every other activation) and
+// is never waited for on the critical path: its 16 result columns are read in the shadow of the next
+// item (or after the loop), so an item costs three exposed MMA round trips instead of four (encoder)
+// or three plus a 144-instruction CUDA-core output layer (decoder).
+//
+// TMEM slot of a chain (128 columns): D [0,64) fp32 | A_h [64,96) packed fp16 hidden activations |
+// A_in [96,112) packed fp16 input row of the next item | D_out [112,128) fp32 output layer.
+// =================================================================================================
+constexpr int kInCol = 96;
+constexpr int kOutCol = 112;
+
+// floor (0) / ceil (1) flavour of corner k per axis, get_neighbors' order (src/models/fusion/utils.py:98-167):
+// k: (f,f,f) (c,f,f) (f,c,f) (f,f,c) (c,c,f) (c,f,c) (f,c,c) (c,c,c)
+__host__ __device__ constexpr int corner_sx(int k) { return (0xB2 >> k) & 1; }
+__host__ __device__ constexpr int corner_sy(int k) { return (0xD4 >> k) & 1; }
+__host__ __device__ constexpr int corner_sz(int k) { return (0xE8 >> k) & 1; }
+
+// one lane of a converged warp (elect.sync): with a warp-uniform enclosing branch and warp-uniform
+// operands ptxas emits straight-line UTCHMMA / UTCBAR; a thread-divergent `if (tid == x)` instead makes it
+// wrap every tcgen05.mma / commit into an ELECT + R2UR.BROADCAST waterfall loop (~45 cycles per MMA and
+// ~250 for the commit, tools/umma_bench2.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+struct RowChain2 {
+  uint32_t t_d, t_a, t_in, t_o;  // this warp's lane base at the slot's D / A_h / A_in / D_out columns
+  uint32_t d_slot;               // slot base (lane 0), for the issuing thread
+  uint64_t* bar_d;               // hidden-layer D complete
+  uint64_t* bar_o;               // output-layer D complete
+  uint32_t par_d, par_o;
+  uint32_t w_saddr;
+  int bar_id;
+  bool issuer_warp;              // warp-uniform: this warp issues the warpgroup's UMMAs (one elected lane)
+};
+
+template <int NWG>
+struct TcShared2 {
+  uint64_t bar_d[NWG];
+  uint64_t bar_o[NWG];
+  uint32_t tmem_base;
+  uint32_t live[NWG][2][4];      // per-warp corner masks of the tile shard (double-buffered)
+};
+
+template <int NWG>
+__device__ __forceinline__ RowChain2 tc_setup2(TcShared2<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
+                                               int w_bytes) {
+  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
+  for (int i = tid * 16; i < w_bytes; i += blockDim.x * 16)
+    *reinterpret_cast<uint4*>(s_weights + i) = __ldg(reinterpret_cast<const uint4*>(g_weights + i));
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < NWG; ++g) {
+      mbar_init(&sh.bar_d[g], 1);
+      mbar_init(&sh.bar_o[g], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&sh.tmem_base, 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  RowChain2 c;
+  // warp-uniform values are broadcast with shfl so that the compiler can keep them in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0), wg_u = warp_u >> 2;
+  c.d_slot = __shfl_sync(0xffffffffu, sh.tmem_base, 0) + wg_u * kSlotCols;
+  c.t_d = c.d_slot + ((uint32_t)((warp_u & 3) * 32) << 16);
+  c.t_a = c.t_d + kACol;
+  c.t_in = c.t_d + kInCol;
+  c.t_o = c.t_d + kOutCol;
+  c.bar_d = &sh.bar_d[wg_u];
+  c.bar_o = &sh.bar_o[wg_u];
+  c.par_d = c.par_o = 0;
+  c.w_saddr = smem_u32(s_weights);
+  c.bar_id = 1 + wg_u;
+  // issuing warps of the four chains sit in different SM sub-partitions (warp % 4)
+  c.issuer_warp = (warp_u & 3) == (wg_u & 3);
+  return c;
+}
+
+template <int NWG>
+__device__ __forceinline__ void tc_teardown2(TcShared2<NWG>& sh) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem_base, 512);
+}
+
+// one K-step of layer (K-major B block at b0, N columns): D[d_col] (+)= A[a_col + 8 kk] * B
+template <int N>
+__device__ __forceinline__ void umma_step(const RowChain2& c, uint32_t b0, int d_col, int a_col, int kk) {
+  constexpr uint32_t lbo = (uint32_t)(N / 8) * 128u;
+  umma_ts_f16(c.d_slot + d_col, c.d_slot + a_col + kk * 8, smem_desc_kmajor(b0 + kk * 2 * lbo, lbo, 128),
+              idesc_f16_m128(N), kk > 0 ? 1u : 0u);
+}
+
+// every thread's TMEM stores / loads of this step are done -> the warpgroup's issuer runs `f`
+template <class F>
+__device__ __forceinline__ void chain2_sync_issue(RowChain2& c, F&& f) {
   tmem_wait_st();
   tc_fence_before();
   wg_sync(c.bar_id);
-  if (c.issuer) {
+  if (c.issuer_warp) {
     tc_fence_after();
-    constexpr uint32_t lbo = (uint32_t)(N / 8) * 128u;
-    constexpr uint32_t idesc = idesc_f16_m128(N);
-    const uint32_t b0 = c.w_saddr + w_off;
-#pragma unroll
-    for (int kk = 0; kk < K / 16; ++kk)
-      umma_ts_f16(c.d_slot, c.d_slot + kACol + kk * 8, smem_desc_kmajor(b0 + kk * 2 * lbo, lbo, 128), idesc,
-                  kk > 0 ? 1u : 0u);
-    umma_commit(c.bar_d);
+    if (elect_one()) f();
   }
 }
-__device__ __forceinline__ void chain_wait_d(RowChain& c) {
+
+// stage the input row of the next item (INW packed fp16x2 words, ones-padded); A_in is free as soon as
+// the L0 of the current item has completed, i.e. any time after the item's first epilogue
+template <int INW>
+__device__ __forceinline__ void chain2_stage(RowChain2& c, const uint32_t (&in)[INW]) {
+  static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
+  if constexpr (INW == 8) tmem_st8(c.t_in, in); else tmem_st16(c.t_in, in);
+}
+
+// first item of a sequence: L0 alone
+template <int INW>
+__device__ __forceinline__ void chain2_begin(RowChain2& c) {
+  chain2_sync_issue(c, [&]() {
+#pragma unroll
+    for (int kk = 0; kk < INW / 8; ++kk) umma_step<64>(c, c.w_saddr, 0, kInCol, kk);
+    umma_commit(c.bar_d);
+  });
+}
+
+__device__ __forceinline__ void chain2_wait_d(RowChain2& c) {
   mbar_wait(c.bar_d, c.par_d);
   c.par_d ^= 1;
   tc_fence_after();
 }
 
-// hidden layer epilogue: D (64 fp32 columns of this row) -> ReLU -> fp16 -> A (32 packed columns)
-__device__ __forceinline__ void chain_hidden_epilogue(RowChain& c) {
+__device__ __forceinline__ void chain2_epilogue(RowChain2& c) {
   uint32_t v[32], w[32];
   tmem_ld32(c.t_d, v);
   tmem_ld32(c.t_d + 32, w);
@@ -270,113 +367,74 @@ __device__ __forceinline__ void chain_hidden_epilogue(RowChain& c) {
   tmem_st32(c.t_a, a);
 }
 
-struct NoShadow {
-  __device__ __forceinline__ void operator()() const {}
-};
+// hidden part of the current item (its L0 is in flight): L0 -> L1 -> L2 -> h3 stored.  `shadow1()` runs
+// right after L1 has been issued, `shadow2()` right after L2: consume the previous item's output
+// (chain2_output) and issue the next item's loads in the first, stage the next item's input
+// (chain2_stage) in the second -- the loads then have a whole round trip to land.
+template <int INW, class Shadow1, class Shadow2>
+__device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, Shadow2&& shadow2) {
+  constexpr int off1 = 2 * INW * 64 * 2, off2 = off1 + 64 * 64 * 2;
+  chain2_wait_d(c);
+  chain2_epilogue(c);
+  chain2_sync_issue(c, [&]() {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off1, 0, kACol, kk);
+    umma_commit(c.bar_d);
+  });
+  shadow1();
+  chain2_wait_d(c);
+  chain2_epilogue(c);
+  chain2_sync_issue(c, [&]() {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off2, 0, kACol, kk);
+    umma_commit(c.bar_d);
+  });
+  shadow2();
+  chain2_wait_d(c);
+  chain2_epilogue(c);
+}
 
-// Run one 128-row tile through the 4-layer MLP.  `in` = this thread's input row as INW packed fp16x2
-// words (ones-padded to in_pad = 2 * INW).  On return `out` holds the first NOUT outputs of the row.
-// Must be called by all 128 threads of the warpgroup.  `shadow()` is invoked once right after the
-// first layer has been issued: work placed there (preparing the next row) runs in the shadow of the
-// MMA round trip (~500 cycles of issue + commit + wake latency, tools/umma_bench.cu).
-//   NOUT == 8 (encoder): all four layers on the tensor core (output layer N = 16).
-//   NOUT == 1 (decoder): the 64 -> 1 output layer is 64 FMAs per row on the CUDA cores, taken from the
-//   fp32 accumulators of layer 2 -- a whole MMA round trip for 0.7 % of the FLOPs is not worth it.
-template <int INW, int NOUT, class Shadow = NoShadow>
-__device__ __forceinline__ void chain_run(RowChain& c, const uint32_t (&in)[INW], float (&out)[NOUT],
-                                          Shadow shadow = Shadow()) {
-  static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
+// output layer of the current item + (has_next) L0 of the staged next item, interleaved in one burst:
+// the two accumulate into different TMEM columns, so their K-steps do not serialise on each other
+template <int INW>
+__device__ __forceinline__ void chain2_finish(RowChain2& c, bool has_next) {
+  constexpr int off3 = 2 * INW * 64 * 2 + 2 * 64 * 64 * 2;
+  chain2_sync_issue(c, [&]() {
+    if (has_next) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        umma_step<16>(c, c.w_saddr + off3, kOutCol, kACol, kk);
+        if (kk < INW / 8) umma_step<64>(c, c.w_saddr, 0, kInCol, kk);
+      }
+      umma_commit(c.bar_o);
+      umma_commit(c.bar_d);
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_step<16>(c, c.w_saddr + off3, kOutCol, kACol, kk);
+      umma_commit(c.bar_o);
+    }
+  });
+}
+
+// read the NOUT outputs of the item whose chain2_finish was issued last (waits for its output layer)
+template <int NOUT>
+__device__ __forceinline__ void chain2_output(RowChain2& c, float (&out)[NOUT]) {
   static_assert(NOUT == 8 || NOUT == 1, "n_out must be 8 or 1");
-  constexpr int KIN = 2 * INW;
-  constexpr int off1 = KIN * 64 * 2, off2 = off1 + 64 * 64 * 2, off3 = off2 + 64 * 64 * 2;
-  if constexpr (INW == 8) tmem_st8(c.t_a, in); else tmem_st16(c.t_a, in);
-  chain_issue_layer<KIN, 64>(c, 0);
-  shadow();
-  chain_wait_d(c);
-  chain_hidden_epilogue(c);
-  chain_issue_layer<64, 64>(c, off1);
-  chain_wait_d(c);
-  chain_hidden_epilogue(c);
-  chain_issue_layer<64, 64>(c, off2);
-  chain_wait_d(c);
+  mbar_wait(c.bar_o, c.par_o);
+  c.par_o ^= 1;
+  tc_fence_after();
   if constexpr (NOUT == 8) {
-    chain_hidden_epilogue(c);
-    chain_issue_layer<64, 16>(c, off3);
-    chain_wait_d(c);
     uint32_t r[8];
-    tmem_ld8(c.t_d, r);
+    tmem_ld8(c.t_o, r);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 8; ++j) out[j] = __uint_as_float(r[j]);
   } else {
-    constexpr int off_w3 = off3 + 16 * 64 * 2;
-    uint32_t v[32], w[32];
-    tmem_ld32(c.t_d, v);
-    tmem_ld32(c.t_d + 32, w);
+    uint32_t r;
+    tmem_ld1(c.t_o, r);
     tmem_wait_ld();
-    const float4* w3 = reinterpret_cast<const float4*>(c.w_gen + off_w3);
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 wa = w3[i], wb = w3[8 + i];
-      acc0 = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]), 0.f), wa.x, acc0);
-      acc1 = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]), 0.f), wa.y, acc1);
-      acc2 = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]), 0.f), wa.z, acc2);
-      acc3 = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]), 0.f), wa.w, acc3);
-      acc0 = fmaf(fmaxf(__uint_as_float(w[4 * i + 0]), 0.f), wb.x, acc0);
-      acc1 = fmaf(fmaxf(__uint_as_float(w[4 * i + 1]), 0.f), wb.y, acc1);
-      acc2 = fmaf(fmaxf(__uint_as_float(w[4 * i + 2]), 0.f), wb.z, acc2);
-      acc3 = fmaf(fmaxf(__uint_as_float(w[4 * i + 3]), 0.f), wb.w, acc3);
-    }
-    out[0] = (acc0 + acc1) + (acc2 + acc3);
+    out[0] = __uint_as_float(r);
   }
-}
-
-// CTA-level setup shared by the tensor-core kernels: NWG row warpgroups, one TMEM slot + mbarrier each
-template <int NWG>
-struct TcShared {
-  uint64_t bar_d[NWG];
-  uint32_t tmem_base;
-};
-
-template <int NWG>
-__device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
-                                             int w_bytes) {
-  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
-  // weights: global -> shared (image is already in the UMMA canonical layout), 16 B per thread step
-  for (int i = tid * 16; i < w_bytes; i += blockDim.x * 16)
-    *reinterpret_cast<uint4*>(s_weights + i) = __ldg(reinterpret_cast<const uint4*>(g_weights + i));
-  if (tid == 0) {
-#pragma unroll
-    for (int g = 0; g < NWG; ++g) mbar_init(&sh.bar_d[g], 1);
-    mbar_fence_init();
-  }
-  if (warp == 0) tmem_alloc(&sh.tmem_base, NWG * kSlotCols);
-  // make the generic-proxy weight stores visible to the tensor core's async-proxy reads
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  RowChain c;
-  const uint32_t base = sh.tmem_base;
-  c.d_slot = base + wg * kSlotCols;
-  c.t_d = c.d_slot + ((uint32_t)((warp & 3) * 32) << 16);
-  c.t_a = c.t_d + kACol;
-  c.bar_d = &sh.bar_d[wg];
-  c.par_d = 0;
-  c.w_saddr = smem_u32(s_weights);
-  c.w_gen = s_weights;
-  c.bar_id = 1 + wg;
-  // issuing threads sit in different SM sub-partitions (warp % 4): the UMMA issue rate is per sub-partition
-  c.issuer = (tid & 127) == 32 * (wg & 3);
-  return c;
-}
-
-template <int NWG>
-__device__ __forceinline__ void tc_teardown(TcShared<NWG>& sh) {
-  tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem_base, NWG * kSlotCols);
 }
 
 }  // namespace tc

@@ -1,0 +1,566 @@
+// tcgen05 kernels on the software-pipelined chain (engine v2, bnv_tc.cuh): plain MLP forward, fused
+// encode (backproject -> 8 corner rows -> encoder MLP -> scatter), fused decode (8-corner gather ->
+// decoder MLP -> trilinear blend + prior) and the G table of the factored meshlize decode.
+//
+// Differences to the first-generation kernels (bnv_tc.cu):
+//  * the output layer runs on the tensor core and is issued together with the next item's first layer;
+//    its result is consumed in the shadow of the next item -> 3 exposed MMA round trips per item;
+//  * the encode kernel splits the frame at (tile, corner) granularity: every chain gets the same number
+//    of corner rows (+-1), which removes the 4-vs-5-tiles tail of the per-tile split;
+//  * in the tile shard, the corners nobody in the warpgroup owns are dropped from the item list up front.
+#include <cuda_fp16.h>
+#include <limits.h>
+#include <stdlib.h>
+
+#include "bnv_common.cuh"
+#include "bnv_decode_common.cuh"
+#include "bnv_frame.cuh"
+#include "bnv_tc.cuh"
+
+using namespace bnv;
+using namespace bnv::tc;
+
+namespace bnv {
+namespace tcc {
+
+constexpr int kNWG = 4;                       // row warpgroups (= chains = TMEM slots) per CTA
+constexpr int kThreads = kNWG * 128;
+constexpr uint32_t kOnes = 0x3C003C00u;       // fp16x2 {1.0, 1.0}: tcnn pads the input with ones
+
+struct alignas(16) Smem {
+  TcShared2<kNWG> sh;
+};
+
+__device__ __forceinline__ uint8_t* weights_smem(uint8_t* smem) { return smem + ((sizeof(Smem) + 127) / 128) * 128; }
+static size_t smem_bytes(int in_pad) { return ((sizeof(Smem) + 127) / 128) * 128 + weight_image(in_pad).bytes; }
+
+static int sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+static int grid_for(int64_t n_items) {
+  const int sms = sm_count();
+  const int64_t need = (n_items + kNWG - 1) / kNWG;
+  return (int)(need < sms ? (need < 1 ? 1 : need) : sms);
+}
+
+// ---- plain forward: items = 128-row tiles --------------------------------------------------------
+template <int NIN, int INW>
+__device__ __forceinline__ void load_row(const float* __restrict__ x, int64_t i, int64_t n, uint32_t (&in)[INW]) {
+  float xi[2 * INW];
+#pragma unroll
+  for (int k = 0; k < 2 * INW; ++k) {
+    const int src = NIN == 17 ? dec_perm(k) : enc_perm(k);       // column order of the packed W0
+    xi[k] = (src < NIN && i < n) ? __ldg(x + i * NIN + src) : 1.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < INW; ++k) in[k] = pack_f16x2(xi[2 * k], xi[2 * k + 1]);
+}
+
+template <int NIN, int INW, int NOUT>
+__global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8_t* __restrict__ gW, int w_bytes,
+                                                                      const float* __restrict__ x, int64_t n,
+                                                                      float* __restrict__ y) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  Smem& S = *reinterpret_cast<Smem*>(smem);
+  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
+  const int64_t n_tiles = (n + 127) / 128;
+  const int64_t stride = (int64_t)gridDim.x * kNWG;
+  int64_t tile = (int64_t)blockIdx.x * kNWG + wg;
+  int64_t pend = -1;                                  // row whose output is still in D_out
+  auto drain = [&]() {
+    if (pend >= 0) {
+      float out[NOUT];
+      chain2_output<NOUT>(c, out);
+      if (pend < n) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) y[pend * NOUT + o] = out[o];
+      }
+    }
+    pend = -1;
+  };
+  if (tile < n_tiles) {
+    uint32_t in[INW];
+    load_row<NIN, INW>(x, tile * 128 + r, n, in);
+    chain2_stage<INW>(c, in);
+    chain2_begin<INW>(c);
+    for (; tile < n_tiles; tile += stride) {
+      const bool has_next = tile + stride < n_tiles;
+      chain2_hidden<INW>(
+          c,
+          [&]() {
+            drain();
+            if (has_next) load_row<NIN, INW>(x, (tile + stride) * 128 + r, n, in);
+          },
+          [&]() {
+            if (has_next) chain2_stage<INW>(c, in);
+          });
+      chain2_finish<INW>(c, has_next);
+      pend = tile * 128 + r;
+    }
+    drain();
+  }
+  tc_teardown2<kNWG>(S.sh);
+}
+
+// ---- fused encode -----------------------------------------------------------------------------------
+// Work unit = (128-point tile, corner).  Chain j of J processes the contiguous unit range
+// [U j / J, U (j + 1) / J): whole tiles in the middle, partial tiles (a corner sub-range) at both ends, so
+// all chains carry the same number of MLP rounds.  Thread r of the warpgroup owns point tile * 128 + r.
+__device__ __forceinline__ void enc_input(int k, const float (&cc)[3], const float (&fl)[3], const float (&ce)[3],
+                                          float vs, float inv_vs, uint32_t nrm01, uint32_t nrm2o, uint32_t (&in)[8]) {
+  float nb[3];
+  corner_of(k, fl, ce, nb);
+  float xr[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float rel = __fmul_rn(__fsub_rn(cc[a], nb[a]), vs);                         // rule A4
+    xr[a] = __fmul_rn(rel, inv_vs);
+  }
+  // row = [x 1 | y 1 | z 1 | n0 n1 | n2 1 | 1 x 6]  (enc_perm: tcnn pads the 6 inputs to 16 with ones)
+  in[0] = pack_f16x2(xr[0], 1.f);
+  in[1] = pack_f16x2(xr[1], 1.f);
+  in[2] = pack_f16x2(xr[2], 1.f);
+  in[3] = nrm01;
+  in[4] = nrm2o;
+  in[5] = in[6] = in[7] = kOnes;
+}
+
+template <bool FROM_DEPTH>
+__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc src, const uint8_t* __restrict__ gW,
+                                                                 int w_bytes, int64_t n_threads,
+                                                                 long long* __restrict__ stats, int debug) {
+  // debug (BNV_DEBUG_ENCODE, profiling ablations only): 1 no MMA chain, 2 no feature reductions,
+  // 4 no claims (+ no reductions), 8 whole tiles per chain instead of the (tile, corner) split
+  extern __shared__ __align__(128) uint8_t smem[];
+  Smem& S = *reinterpret_cast<Smem*>(smem);
+  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5;
+  const GeomDev& g = m.g;
+  const int64_t n_units = ((n_threads + 127) / 128) * 8;
+  const int64_t chain = (int64_t)blockIdx.x * kNWG + wg, n_chains = (int64_t)gridDim.x * kNWG;
+  const int64_t u_end = n_units * (chain + 1) / n_chains;
+  int st_valid = 0, st_inb = 0, st_rows = 0;           // frame statistics, flushed once per warp at the end
+  int32_t pend_slot = -1;
+  bool pending = false;                                // an output layer is in flight / unread in D_out
+  int flip = 0;
+  auto drain = [&]() {
+    if (pending) {
+      float y[8];
+      if (debug & 1) { for (int j = 0; j < 8; ++j) y[j] = (float)j; } else
+      chain2_output<8>(c, y);
+      if (pend_slot >= 0 && !(debug & 6)) add_row_f32(m, pend_slot, y);
+      pending = false;
+    }
+  };
+  int64_t u_begin = n_units * chain / n_chains, u_stop = u_end, u_step = 0;
+  if (debug & 8) { u_begin = chain * 8; u_stop = n_units; u_step = (n_chains - 1) * 8; }
+  for (int64_t u = u_begin; u < u_stop; u += u_step) {
+    const int64_t tile = u >> 3;
+    const int k0 = (int)(u & 7);
+    const int k1 = (int)(u_stop - u < (int64_t)(8 - k0) ? k0 + (u_stop - u) : 8);
+    u += k1 - k0;
+    const int64_t idx = tile * 128 + r;
+    float p[6];
+    bool valid = false;
+    if (FROM_DEPTH) {
+      if (idx < n_threads)
+        valid = backproject_pixel(src.depth, src.cam, (int)(idx % src.cam.W), (int)(idx / src.cam.W), p);
+    } else if (idx < n_threads) {
+      valid = true;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
+    }
+    bool inb = valid;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) inb = inb && (p[a] < g.hi[a]) && (p[a] > g.lo[a]);     // rule A1
+    float cc[3], fl[3], ce[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      cc[a] = inb ? __fmul_rn(__fsub_rn(p[a], g.bmin[a]), g.inv_vs) : 0.f;             // rule A2
+      fl[a] = floorf(cc[a]);
+      ce[a] = ceilf(cc[a]);
+    }
+    const uint32_t nrm01 = pack_f16x2(inb ? p[3] : 0.f, inb ? p[4] : 0.f);
+    const uint32_t nrm2o = pack_f16x2(inb ? p[5] : 0.f, 1.f);
+    // claim the scratch rows of this chain's corners (independent CAS round trips in flight)
+    int32_t slot[8];
+    uint32_t own = 0;
+    int n_rows = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float nb[3];
+      corner_of(k, fl, ce, nb);
+      const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
+      slot[k] = -1;
+      if (k >= k0 && k < k1 && inb && owns(g, ix, iy, iz)) {
+        slot[k] = (debug & 4) ? 0 : claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
+        own |= 1u << k;
+        ++n_rows;
+      }
+    }
+    if (k0 == 0) {
+      st_valid += valid ? 1 : 0;
+      st_inb += inb ? 1 : 0;
+    }
+    st_rows += n_rows;
+    // corners to run: all of [k0, k1) on one GPU; in the tile shard only those somebody here owns
+    uint32_t live = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
+    if (g.world > 1) {
+      const uint32_t wown = __reduce_or_sync(0xffffffffu, own);
+      if ((r & 31) == 0) S.sh.live[wg][flip][warp_in_wg] = wown;
+      wg_sync(c.bar_id);
+      live = S.sh.live[wg][flip][0] | S.sh.live[wg][flip][1] | S.sh.live[wg][flip][2] | S.sh.live[wg][flip][3];
+      flip ^= 1;
+    }
+    if (live == 0) continue;
+    // the chain is idle here (the previous tile's last corner was finished without a next item; its
+    // output, if still unread, is drained in the shadow of this tile's first corner)
+    {
+      uint32_t in[8];
+      enc_input(__ffs(live) - 1, cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
+      chain2_stage<8>(c, in);
+      if (!(debug & 1)) chain2_begin<8>(c);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!((live >> k) & 1u)) continue;
+      const uint32_t rest = live >> (k + 1);
+      const bool has_next = rest != 0;
+      if (debug & 1) { drain(); pending = true; pend_slot = slot[k]; continue; }
+      chain2_hidden<8>(
+          c, [&]() { drain(); },
+          [&]() {
+            if (has_next) {
+              uint32_t in[8];
+              enc_input(k + __ffs(rest), cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
+              chain2_stage<8>(c, in);
+            }
+          });
+      chain2_finish<8>(c, has_next);
+      pending = true;
+      pend_slot = slot[k];
+    }
+  }
+  drain();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
+    st_inb += __shfl_xor_sync(0xffffffffu, st_inb, o);
+    st_rows += __shfl_xor_sync(0xffffffffu, st_rows, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (st_valid | st_inb | st_rows)) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)st_valid);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)st_rows);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)st_inb);
+  }
+  tc_teardown2<kNWG>(S.sh);
+}
+
+// ---- fused decode -----------------------------------------------------------------------------------
+struct AxisPre {       // one axis of a query, floor (s = 0) and ceil (s = 1) flavours
+  uint32_t w_ls[2];    // fp16x2 {l, sin l}
+  uint32_t w_c1[2];    // fp16x2 {cos l, 1}
+  float t[2];          // 1 - |l|
+  int32_t tab[2];      // voxel index * table stride of this axis, or INT_MIN when outside the grid
+  int32_t ts[2];       // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint4* __restrict__ packed,
+                                                                 const uint8_t* __restrict__ gW, int w_bytes) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  Smem& S = *reinterpret_cast<Smem*>(smem);
+  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
+  const int64_t n_tiles = (a.n_queries + 127) / 128;
+  const GeomDev& g = m.g;
+  constexpr int32_t kOut = INT_MIN;
+  // the query whose last corner is still in D_out
+  bool pending = false, p_live = false;
+  int64_t p_q = 0;
+  float p_sdf = 0.f, p_dsum = 0.f, p_minw = 0.f, p_wn = 0.f, p_dl = 0.f;
+  auto drain = [&]() {
+    if (pending) {
+      float y[1];
+      chain2_output<1>(c, y);
+      p_sdf = __fadd_rn(p_sdf, __fmul_rn(__fmul_rn(y[0], g.vs), p_wn));                   // D4, D5 (corner 7)
+      if (a.tsdf) p_dsum = __fadd_rn(p_dsum, __fmul_rn(p_dl, p_wn));                     // D6
+      if (p_live) {
+        bool mask;
+        a.out_sdf[p_q] = finish_blend(p_sdf, p_dsum, p_minw, a, g.vs, &mask);
+        if (a.out_mask) a.out_mask[p_q] = mask ? 1 : 0;
+      }
+      pending = false;
+    }
+  };
+  for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
+    const int64_t q = tile * 128 + r;
+    const bool live = q < a.n_queries;
+    float cq[3] = {0.f, 0.f, 0.f};
+    if (live) query_coords(m, a, q, cq);
+    // ---- once per query: everything that depends on one axis only ---------------------------------
+    AxisPre ax[3];
+    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
+    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float nbv[2] = {floorf(cq[d]), ceilf(cq[d])};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float l = __fsub_rn(cq[d], nbv[s]);                                        // D1
+        float sn, cs;
+        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
+        ax[d].w_ls[s] = pack_f16x2(l, sn);
+        ax[d].w_c1[s] = pack_f16x2(cs, 1.0f);
+        ax[d].t[s] = __fsub_rn(1.f, fabsf(l));
+        const int iv = (int)nbv[s];
+        ax[d].tab[s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
+        ax[d].ts[s] = kOut;
+        if (a.tsdf) {                                                                    // grid_sample(nearest), D6
+          float t = __fdiv_rn(nbv[s], a.nm1[d]);
+          t = __fmul_rn(t, 2.f);
+          t = __fsub_rn(t, 1.f);
+          t = __fadd_rn(t, 1.f);
+          t = __fmul_rn(t, 0.5f);
+          t = __fmul_rn(t, a.tm1[d]);
+          const float rr = nearbyintf(t);
+          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ax[d].ts[s] = (int)rr * pstride[d];
+        }
+      }
+    }
+    float wsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float w = __fmul_rn(__fmul_rn(ax[0].t[corner_sx(k)], ax[1].t[corner_sy(k)]), ax[2].t[corner_sz(k)]);
+      wsum = k == 0 ? w : __fadd_rn(wsum, w);                                            // D2 normaliser
+    }
+    // ---- 8 independent table lookups in flight (_query_tensor, D3) ---------------------------------
+    int32_t slot[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int32_t tx = ax[0].tab[corner_sx(k)], ty = ax[1].tab[corner_sy(k)], tz = ax[2].tab[corner_sz(k)];
+      slot[k] = kEmpty;
+      if (tx != kOut && ty != kOut && tz != kOut) slot[k] = __ldg(m.table + ((int64_t)tx + ty + tz));
+    }
+    uint4 f_nxt = make_uint4(0, 0, 0, 0);
+    float w_nxt = 0.f, w_cur = 0.f;
+    if (slot[0] >= 0 && slot[0] < a.n_rows) {
+      f_nxt = __ldg(packed + slot[0]);
+      w_nxt = __ldg(a.weights_rows + slot[0]);
+    }
+    // the previous query's last corner has been in flight during all of the above
+    drain();
+    float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
+    {
+      const uint32_t in[16] = {f_nxt.x, f_nxt.y, f_nxt.z, f_nxt.w,
+                               ax[0].w_ls[0], ax[0].w_c1[0], ax[1].w_ls[0], ax[1].w_c1[0],
+                               ax[2].w_ls[0], ax[2].w_c1[0], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+      chain2_stage<16>(c, in);
+      chain2_begin<16>(c);
+      w_cur = w_nxt;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      minw = fminf(minw, w_cur);                                                         // D3
+      chain2_hidden<16>(
+          c,
+          [&]() {
+            // shadow of the second layer: issue the next corner's gather, blend the previous corner
+            if (k < 7) {
+              f_nxt = make_uint4(0, 0, 0, 0);
+              w_nxt = 0.f;
+              const int32_t s = slot[k < 7 ? k + 1 : 7];
+              if (s >= 0 && s < a.n_rows) {
+                f_nxt = __ldg(packed + s);
+                w_nxt = __ldg(a.weights_rows + s);
+              }
+            }
+            if (k > 0) {
+              const int kp = k > 0 ? k - 1 : 0;
+              float y[1];
+              chain2_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
+              const float wk = __fmul_rn(__fmul_rn(ax[0].t[corner_sx(kp)], ax[1].t[corner_sy(kp)]), ax[2].t[corner_sz(kp)]);
+              const float wn = __fdiv_rn(wk, wsum);                                      // D2
+              sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                // D4, D5
+              if (a.tsdf) {
+                const int32_t px = ax[0].ts[corner_sx(kp)], py = ax[1].ts[corner_sy(kp)], pz = ax[2].ts[corner_sz(kp)];
+                const float dl = (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
+                dsum = __fadd_rn(dsum, __fmul_rn(dl, wn));                               // D6
+              }
+            }
+          },
+          [&]() {
+            // shadow of the third layer: the gather has landed -> stage the next corner's row
+            if (k < 7) {
+              const int kn = k < 7 ? k + 1 : 7;
+              const uint32_t in[16] = {f_nxt.x, f_nxt.y, f_nxt.z, f_nxt.w,
+                                       ax[0].w_ls[corner_sx(kn)], ax[0].w_c1[corner_sx(kn)],
+                                       ax[1].w_ls[corner_sy(kn)], ax[1].w_c1[corner_sy(kn)],
+                                       ax[2].w_ls[corner_sz(kn)], ax[2].w_c1[corner_sz(kn)],
+                                       kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+              chain2_stage<16>(c, in);
+            }
+          });
+      chain2_finish<16>(c, k < 7);
+      w_cur = w_nxt;
+    }
+    // corner 7 is in flight: finish this query at the top of the next tile (or after the loop)
+    pending = true;
+    p_live = live;
+    p_q = q;
+    p_sdf = sdf;
+    p_dsum = dsum;
+    p_minw = minw;
+    p_wn = __fdiv_rn(__fmul_rn(__fmul_rn(ax[0].t[1], ax[1].t[1]), ax[2].t[1]), wsum);
+    p_dl = 0.f;
+    if (a.tsdf) {
+      const int32_t px = ax[0].ts[1], py = ax[1].ts[1], pz = ax[2].ts[1];
+      if (px != kOut && py != kOut && pz != kOut) p_dl = __ldg(a.tsdf + ((int64_t)px + py + pz));
+    }
+  }
+  drain();
+  tc_teardown2<kNWG>(S.sh);
+}
+
+// ---- factored decode of the meshlize sample blocks: G[V][l] table (see bnv_tc.cu) ----------------------
+__global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __restrict__ packed, int64_t n_rows,
+                                                                 const uint8_t* __restrict__ gW, int w_bytes,
+                                                                 float* __restrict__ G) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  Smem& S = *reinterpret_cast<Smem*>(smem);
+  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
+  const int64_t total = (n_rows + 1) * 27;                       // voxel n_rows = the miss voxel
+  const int64_t n_tiles = (total + 127) / 128;
+  const int64_t stride = (int64_t)gridDim.x * kNWG;
+  uint32_t w_ls[3], w_c1[3];                                     // l = -0.5, 0, +0.5
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float l = 0.5f * (float)(d - 1);
+    float sn, cs;
+    __sincosf(l, &sn, &cs);
+    w_ls[d] = pack_f16x2(l, sn);
+    w_c1[d] = pack_f16x2(cs, 1.0f);
+  }
+  auto make_row = [&](int64_t row, uint32_t (&in)[16]) {
+    const int64_t v = row / 27;
+    const int li = (int)(row - v * 27);
+    uint4 f = make_uint4(0, 0, 0, 0);
+    if (row < total && v < n_rows) f = __ldg(packed + v);
+    const int dx = li / 9, dy = (li / 3) % 3, dz = li % 3;
+    // dynamic index into 3-element register arrays -> selects
+    const uint32_t lx = dx == 0 ? w_ls[0] : dx == 1 ? w_ls[1] : w_ls[2], cx = dx == 0 ? w_c1[0] : dx == 1 ? w_c1[1] : w_c1[2];
+    const uint32_t ly = dy == 0 ? w_ls[0] : dy == 1 ? w_ls[1] : w_ls[2], cy = dy == 0 ? w_c1[0] : dy == 1 ? w_c1[1] : w_c1[2];
+    const uint32_t lz = dz == 0 ? w_ls[0] : dz == 1 ? w_ls[1] : w_ls[2], cz = dz == 0 ? w_c1[0] : dz == 1 ? w_c1[1] : w_c1[2];
+    in[0] = f.x; in[1] = f.y; in[2] = f.z; in[3] = f.w;
+    in[4] = lx; in[5] = cx; in[6] = ly; in[7] = cy; in[8] = lz; in[9] = cz;
+#pragma unroll
+    for (int j = 10; j < 16; ++j) in[j] = kOnes;
+  };
+  int64_t tile = (int64_t)blockIdx.x * kNWG + wg;
+  int64_t pend = -1;
+  auto drain = [&]() {
+    if (pend >= 0) {
+      float y[1];
+      chain2_output<1>(c, y);
+      if (pend < total) G[pend] = y[0];
+    }
+    pend = -1;
+  };
+  if (tile < n_tiles) {
+    uint32_t in[16];
+    make_row(tile * 128 + r, in);
+    chain2_stage<16>(c, in);
+    chain2_begin<16>(c);
+    for (; tile < n_tiles; tile += stride) {
+      const bool has_next = tile + stride < n_tiles;
+      chain2_hidden<16>(
+          c,
+          [&]() {
+            drain();
+            if (has_next) make_row((tile + stride) * 128 + r, in);
+          },
+          [&]() {
+            if (has_next) chain2_stage<16>(c, in);
+          });
+      chain2_finish<16>(c, has_next);
+      pend = tile * 128 + r;
+    }
+    drain();
+  }
+  tc_teardown2<kNWG>(S.sh);
+}
+
+}  // namespace tcc
+}  // namespace bnv
+
+// ---- host side ------------------------------------------------------------------------------------------
+using namespace bnv::tcc;
+
+template <typename Kern>
+static int set_smem(Kern k, size_t bytes) {
+  BNV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return BNV_OK;
+}
+
+int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s) {
+  const size_t smem = smem_bytes(mlp->in_pad);
+  const int grid = grid_for((n + 127) / 128);
+  if (mlp->n_in == 6) {
+    int rc = set_smem(mlp_forward_tc_kernel<6, 8, 8>, smem);
+    if (rc) return rc;
+    mlp_forward_tc_kernel<6, 8, 8><<<grid, kThreads, smem, s>>>((const uint8_t*)mlp->w16, (int)mlp->w16_bytes, x, n, y);
+  } else {
+    int rc = set_smem(mlp_forward_tc_kernel<17, 16, 1>, smem);
+    if (rc) return rc;
+    mlp_forward_tc_kernel<17, 16, 1><<<grid, kThreads, smem, s>>>((const uint8_t*)mlp->w16, (int)mlp->w16_bytes, x, n, y);
+  }
+  BNV_LAUNCH_CHECK("mlp_forward_tc_kernel");
+  return BNV_OK;
+}
+
+int bnv_internal_encode_chain(bnv_map_t* map, const void* srcp, int from_depth, int64_t n_threads, const bnv_mlp_t* enc,
+                            cudaStream_t s) {
+  const EncSrc& src = *reinterpret_cast<const EncSrc*>(srcp);
+  const char* e = getenv("BNV_DEBUG_ENCODE");     // profiling experiments only
+  const int dbg = e ? atoi(e) : 0;
+  const size_t smem = smem_bytes(enc->in_pad);
+  const int grid = grid_for(((n_threads + 127) / 128) * 8);        // units = (tile, corner)
+  if (from_depth) {
+    int rc = set_smem(encode_tc_kernel<true>, smem);
+    if (rc) return rc;
+    encode_tc_kernel<true><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
+                                                         n_threads, (long long*)map->stats, dbg);
+  } else {
+    int rc = set_smem(encode_tc_kernel<false>, smem);
+    if (rc) return rc;
+    encode_tc_kernel<false><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
+                                                          n_threads, (long long*)map->stats, dbg);
+  }
+  BNV_LAUNCH_CHECK("encode_tc_kernel");
+  return BNV_OK;
+}
+
+int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
+  const size_t smem = smem_bytes(dec->in_pad);
+  int rc = set_smem(decode_tc_kernel, smem);
+  if (rc) return rc;
+  decode_tc_kernel<<<grid_for((a.n_queries + 127) / 128), kThreads, smem, s>>>(
+      map->d, a, (const uint4*)map->dec_pack, (const uint8_t*)dec->w16, (int)dec->w16_bytes);
+  BNV_LAUNCH_CHECK("decode_tc_kernel");
+  return BNV_OK;
+}
+
+int bnv_internal_gtable_chain(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s) {
+  const size_t smem = smem_bytes(dec->in_pad);
+  int rc = set_smem(gtable_tc_kernel, smem);
+  if (rc) return rc;
+  const int64_t tiles = ((n_rows + 1) * 27 + 127) / 128;
+  gtable_tc_kernel<<<grid_for(tiles), kThreads, smem, s>>>((const uint4*)map->dec_pack, n_rows, (const uint8_t*)dec->w16,
+                                                            (int)dec->w16_bytes, (float*)map->gtable);
+  BNV_LAUNCH_CHECK("gtable_tc_kernel");
+  return BNV_OK;
+}

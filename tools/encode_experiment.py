@@ -27,6 +27,6 @@ def run(kind):
     ts = np.array(ts[4:]); return ts.mean(0)
 print("RESULT", os.environ.get("BNV_DEBUG_ENCODE", "0"), "depth enc/fin ms", run("depth").round(4).tolist(), "points enc/fin ms", run("points").round(4).tolist())
 '''
-for dbg in ("0", "5"):
+for dbg in (sys.argv[1:] or ["0"]):
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BNV_DEBUG_ENCODE=dbg), capture_output=True, text=True)
     print([l for l in r.stdout.splitlines() if l.startswith("RESULT")] or r.stderr[-400:])
