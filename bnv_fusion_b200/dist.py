@@ -93,7 +93,7 @@ def select_needed(flat, n_xyz, rank, world, brick_log2):
 class TileShardedFusion:
     """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
 
-    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None):
+    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None, overlap=True):
         import torch
         from . import _lib
         self.torch, self._lib = torch, _lib
@@ -103,21 +103,60 @@ class TileShardedFusion:
         self.group = group
         words = HEADER_WORDS + self.capacity * RECORD_WORDS
         dev = volume.device
-        self.halo = torch.zeros(words, dtype=torch.int32, device=dev)
-        self.gathered = torch.zeros(words * self.world, dtype=torch.int32, device=dev)
+        # two buffer pairs: the exchange of frame f runs on a side stream while frame f + 1 is fused
+        self.halo = [torch.zeros(words, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.gathered = [torch.zeros(words * self.world, dtype=torch.int32, device=dev) for _ in range(2)]
+        self.done = [None, None]                 # side-stream event: exchange that last used pair i finished
+        self.flip = 0
+        self.overlap = bool(overlap) and self.world > 1
+        self.side = torch.cuda.Stream(device=dev) if self.overlap else None
         volume.set_shard(self.rank, self.world, self.brick_log2)
-        _lib.check(volume._lib.bnv_map_set_halo_buffer(volume._handle, _lib.ptr(self.halo), self.capacity),
-                   "bnv_map_set_halo_buffer")
+        volume._halo_sync = self.synchronize     # SparseVolume reads (to_tensor, decode) wait for the halo
+        self._attach(0)
+
+    def _attach(self, i):
+        v = self.volume
+        self._lib.check(v._lib.bnv_map_set_halo_buffer(v._handle, self._lib.ptr(self.halo[i]), self.capacity),
+                        "bnv_map_set_halo_buffer")
 
     def fuse_depth_frame(self, depth_mm, K, T_wc, max_depth=3.0, stats=None, navg=None):
+        """Fuse one frame into this rank's tiles, then exchange the boundary voxels (ONE all-gather).
+
+        Integration only ever touches voxels this rank owns, halo copies are only read by decode: the
+        all-gather + halo upsert of frame f therefore runs on a side stream, overlapped with the fusion of
+        frame f + 1; `synchronize()` (called by the volume's read paths) joins the two streams."""
         import torch.distributed as dist
+        torch = self.torch
         v, lib = self.volume, self._lib
+        i = self.flip
+        main = torch.cuda.current_stream(v.device)
+        if self.done[i] is not None:             # the exchange two frames ago used this buffer pair
+            main.wait_event(self.done[i])
+        self._attach(i)
         lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
         self.model.fuse_depth_frame(v, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg)
         if self.world > 1:
-            dist.all_gather_into_tensor(self.gathered, self.halo, group=self.group)   # the one collective
-            lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered), self.world, self.capacity,
-                                                 v._stream()), "bnv_map_insert_halo")
+            if not self.overlap:
+                dist.all_gather_into_tensor(self.gathered[i], self.halo[i], group=self.group)   # the one collective
+                lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered[i]), self.world, self.capacity,
+                                                     v._stream()), "bnv_map_insert_halo")
+            else:
+                fused = main.record_event()
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(fused)
+                    dist.all_gather_into_tensor(self.gathered[i], self.halo[i], group=self.group)   # the one collective
+                    lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered[i]), self.world,
+                                                         self.capacity, C.c_void_p(self.side.cuda_stream)),
+                              "bnv_map_insert_halo")
+                    self.done[i] = self.side.record_event()
+        self.flip ^= 1
+
+    def synchronize(self):
+        """the current stream waits for every halo exchange issued so far"""
+        main = self.torch.cuda.current_stream(self.volume.device)
+        for ev in self.done:
+            if ev is not None:
+                main.wait_event(ev)
 
     def owned_rows(self):
         """bool mask over the rows of volume.to_tensor(): voxels this rank owns (not halo copies)"""
@@ -125,4 +164,6 @@ class TileShardedFusion:
         return (c.sum(dim=1) % self.world) == self.rank
 
     def detach(self):
+        self.synchronize()
+        self.volume._halo_sync = None
         self._lib.check(self.volume._lib.bnv_map_set_halo_buffer(self.volume._handle, None, 0), "detach halo")

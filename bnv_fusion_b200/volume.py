@@ -147,17 +147,24 @@ class SparseVolume:
         self.active_coordinates = None
 
     def __len__(self):
+        self._join_halo()
         n = C.c_int64(0)
         _lib.check(self._lib.bnv_map_size(self._handle, C.byref(n), self._stream()), "bnv_map_size")
         return int(n.value)
 
     def check_status(self):
         """Raise if a device-side fault (capacity overflow / out-of-grid key) was latched."""
+        self._join_halo()
         _lib.check(self._lib.bnv_map_status(self._handle, self._stream()), "bnv_map_status")
 
     def set_shard(self, rank, world, brick_log2=4):
         _lib.check(self._lib.bnv_map_set_shard(self._handle, int(rank), int(world), int(brick_log2)),
                    "bnv_map_set_shard")
+
+    def _join_halo(self):
+        sync = getattr(self, "_halo_sync", None)      # tile shard: pending boundary exchanges (dist.py)
+        if sync is not None:
+            sync()
 
     def to_tensor(self):
         """store all active values to pytorch tensors (sparse_volume.py:525-559).

@@ -29,9 +29,10 @@ def _setup(dev):
     return m
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode):
     import torch.distributed as dist
-    from bnv_fusion_b200 import synth
+    from bnv_fusion_b200 import synth, config
+    config.set_mlp_mode(mode)
     from bnv_fusion_b200.dist import TileShardedFusion
     from bnv_fusion_b200.volume import SparseVolume
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -61,14 +62,27 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_tile_shard(tmp_path):
+@pytest.mark.parametrize("mode", ["fp32", "tc16"])
+def test_two_gpu_tile_shard(tmp_path, mode):
+    """fp32 mode (order-independent fixed-point sums): owned + halo values bit-identical to one GPU.
+    tc16 mode (fp32 `red.add` partial sums, arrival order differs between runs): same voxels, values to
+    summation-order noise."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    from bnv_fusion_b200 import synth
+    from bnv_fusion_b200 import synth, config
     from bnv_fusion_b200.volume import SparseVolume
     world = 2
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path), mode), nprocs=world, join=True)
+    config.set_mlp_mode(mode)
+    exact = mode == "fp32"
+
+    def same(a, b, tol):
+        if exact:
+            return np.array_equal(a, b)
+        assert np.abs(a - b).max() <= tol, np.abs(a - b).max()
+        return True
+
     dev = "cuda:0"
     model = _setup(dev)
     spec = synth.stream_spec("lounge")
@@ -94,15 +108,16 @@ def test_two_gpu_tile_shard(tmp_path):
         f = c[:, 0] * 512 * 512 + c[:, 1] * 512 + c[:, 2]
         pos = np.searchsorted(ref["flat"], f)
         assert np.array_equal(ref["flat"][pos], f)                     # no voxel the single-GPU map lacks
-        assert np.array_equal(z["feats"], ref["feats"][pos])           # bit-identical values (owned + halo)
+        assert same(z["feats"], ref["feats"][pos], 5e-5)               # owned + halo values
         assert np.array_equal(z["weights"][:, 0], ref["w"][pos])
         own = z["own"]
         assert (~own).sum() > 0                                         # halo copies exist
         from bnv_fusion_b200 import dist as D
         assert D.on_brick_shell(c[~own], 4).all()                       # ... only brick shells
         # SDF of the own voxels' 27 samples == single GPU (needs the halo to be complete)
-        assert np.array_equal(z["blocks"][own], ref["blocks"][pos][own])
+        assert same(z["blocks"][own], ref["blocks"][pos][own], 1e-4)
         owned_flat.append(f[own])
         total_rows += int(z["rows"])
     assert np.array_equal(np.sort(np.concatenate(owned_flat)), ref["flat"])
     assert total_rows == rows                                           # the MLP rows were divided, not duplicated
+    config.set_mlp_mode("tc16")
