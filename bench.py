@@ -225,7 +225,7 @@ def run_b200(args):
     sampler.start()
     launches0 = lib.bnv_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    enc_ms, fin_ms, rows_total = [], [], 0
+    enc_ms, fin_ms, rows_total, touched_total, kept_total = [], [], 0, 0, 0
     barrier()
     for i in range(args.steps):
         flush.zero_()
@@ -235,7 +235,8 @@ def run_b200(args):
         a, b = C.c_float(), C.c_float()
         _lib.check(lib.bnv_map_get_timing(vol._handle, C.byref(a), C.byref(b)), "timing")
         enc_ms.append(a.value); fin_ms.append(b.value)
-        rows_total += int(stats[1])
+        st = stats.tolist()
+        rows_total += int(st[1]); touched_total += int(st[2]); kept_total += int(st[3])
     barrier()
     launches = lib.bnv_launch_count() - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
@@ -344,6 +345,7 @@ def run_b200(args):
     enc_avg = float(np.mean(enc_ms))
     rows_per_launch = rows_total / args.steps
     enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
+    scatter_bytes = 2 * H * W + 64 + touched_total / args.steps * 44 + kept_total / args.steps * 80
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         fps, dt = cpu_port(spec, frames, 2, 60)
@@ -384,6 +386,16 @@ def run_b200(args):
                          "traffic": traffic("encode_tc_kernel" if config.mlp_mode_name() == "tc16" else "encode_simt_kernel"),
                          "peak_source": pk["src"],
                          "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "finalize_ms": float(np.mean(fin_ms))},
+            # the scatter stage is "HBM-bound by contract"; with ~10 MB of algorithmic traffic per frame
+            # it is nowhere near the HBM roof (latency / L2-atomic bound), reported for completeness
+            "roofline_hbm": {"kernel": "encode + finalize (scatter / upsert stage)", "bound": "hbm",
+                             "achieved": scatter_bytes / ((enc_avg + float(np.mean(fin_ms))) * 1e-3) / 1e9,
+                             "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": scatter_bytes / ((enc_avg + float(np.mean(fin_ms))) * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "algorithmic_bytes_per_launch": scatter_bytes,
+                             "traffic": traffic("encode_tc_kernel" if config.mlp_mode_name() == "tc16" else "encode_simt_kernel"),
+                             "note": "bytes = 2*H*W (uint16 depth) + 64 + M_t*44 + M*80 (SURVEY 8d with the uint16 depth "
+                                     "image this path reads); M_t, M from the frame statistics"},
             "decode": {"value": n_q_job / (dec_ms_job * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_q_job,
                        "active_voxels_rank0": A, "ms": dec_ms_job,
                        "path": "bnv_decode_voxel_blocks (meshlize samples): G[voxel][offset] table on the tensor cores + blend",

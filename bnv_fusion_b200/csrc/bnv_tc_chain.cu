@@ -29,6 +29,7 @@ constexpr uint32_t kOnes = 0x3C003C00u;       // fp16x2 {1.0, 1.0}: tcnn pads th
 
 struct alignas(16) Smem {
   TcShared2<kNWG> sh;
+  int32_t slot[8][kThreads];   // encode: scratch row of (this thread's point, corner k); thread-private, [k][tid]
 };
 
 __device__ __forceinline__ uint8_t* weights_smem(uint8_t* smem) { return smem + ((sizeof(Smem) + 127) / 128) * 128; }
@@ -152,6 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       float y[8];
       if (debug & 1) { for (int j = 0; j < 8; ++j) y[j] = (float)j; } else
       chain2_output<8>(c, y);
+      if (debug & 16) { if (!(debug & 6)) add_row_f32_runs(m, pend_slot, y); } else
       if (pend_slot >= 0 && !(debug & 6)) add_row_f32(m, pend_slot, y);
       pending = false;
     }
@@ -186,27 +188,58 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     }
     const uint32_t nrm01 = pack_f16x2(inb ? p[3] : 0.f, inb ? p[4] : 0.f);
     const uint32_t nrm2o = pack_f16x2(inb ? p[5] : 0.f, 1.f);
-    // claim the scratch rows of this chain's corners (independent CAS round trips in flight)
-    int32_t slot[8];
+    // claim the scratch rows of this chain's corners: the CAS round trips are only ISSUED here (8 in
+    // flight per thread); their results are consumed in the shadow of the tile's first MLP round
+    // (`settle`), so neither the CAS latency nor the first-touch bookkeeping sits on the chain's critical path
+    int32_t old[8];
     uint32_t own = 0;
-    int n_rows = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float nb[3];
       corner_of(k, fl, ce, nb);
       const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-      slot[k] = -1;
+      old[k] = -2;
       if (k >= k0 && k < k1 && inb && owns(g, ix, iy, iz)) {
-        slot[k] = (debug & 4) ? 0 : claim_row(m, ix * g.nyz + iy * g.n[2] + iz, (int32_t)(idx * 8 + k));      // rule A5
         own |= 1u << k;
-        ++n_rows;
+        old[k] = (debug & 4) ? 0 : atomicCAS(&m.ftable[ix * g.nyz + iy * g.n[2] + iz], kEmpty, (int32_t)(idx * 8 + k));   // rule A5
       }
     }
+    // first-touch bookkeeping of the claimed rows: ONE counter atomic per warp (warp prefix sum)
+    auto settle = [&]() {
+      int n_new = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) n_new += (((own >> k) & 1u) && old[k] == kEmpty) ? 1 : 0;
+      const int lane = threadIdx.x & 31;
+      int incl = n_new;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int base = 0;
+      if (lane == 31 && incl > 0) base = atomicAdd(&m.ctr[1], incl);
+      int pos = __shfl_sync(0xffffffffu, base, 31) + incl - n_new;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int32_t sl = -1;
+        if ((own >> k) & 1u) {
+          sl = old[k];
+          if (sl == kEmpty) {
+            float nb[3];
+            corner_of(k, fl, ce, nb);
+            sl = (int32_t)(idx * 8 + k);
+            m.fkeys[sl] = (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2];
+            m.touched[pos++] = sl;
+          }
+        }
+        S.slot[k][threadIdx.x] = sl;
+      }
+    };
     if (k0 == 0) {
       st_valid += valid ? 1 : 0;
       st_inb += inb ? 1 : 0;
     }
-    st_rows += n_rows;
+    st_rows += __popc(own);
     // corners to run: all of [k0, k1) on one GPU; in the tile shard only those somebody here owns
     uint32_t live = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
     if (g.world > 1) {
@@ -216,33 +249,48 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       live = S.sh.live[wg][flip][0] | S.sh.live[wg][flip][1] | S.sh.live[wg][flip][2] | S.sh.live[wg][flip][3];
       flip ^= 1;
     }
-    if (live == 0) continue;
+    if (live == 0) continue;              // nobody here owns anything of this tile: `own` is 0 for every thread
+    if (debug & 1) {                      // ablation: no MMA chain
+      drain();
+      settle();
+      for (uint32_t rem = live; rem; rem &= rem - 1) {
+        drain();
+        pending = true;
+        pend_slot = S.slot[__ffs(rem) - 1][threadIdx.x];
+      }
+      continue;
+    }
     // the chain is idle here (the previous tile's last corner was finished without a next item; its
     // output, if still unread, is drained in the shadow of this tile's first corner)
     {
       uint32_t in[8];
       enc_input(__ffs(live) - 1, cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
       chain2_stage<8>(c, in);
-      if (!(debug & 1)) chain2_begin<8>(c);
+      chain2_begin<8>(c);
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (!((live >> k) & 1u)) continue;
-      const uint32_t rest = live >> (k + 1);
-      const bool has_next = rest != 0;
-      if (debug & 1) { drain(); pending = true; pend_slot = slot[k]; continue; }
+    bool first = true;
+#pragma unroll 1
+    for (uint32_t rem = live; rem;) {
+      const int k = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const bool has_next = rem != 0;
       chain2_hidden<8>(
-          c, [&]() { drain(); },
+          c,
+          [&]() {
+            drain();
+            if (first) settle();
+          },
           [&]() {
             if (has_next) {
               uint32_t in[8];
-              enc_input(k + __ffs(rest), cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
+              enc_input(__ffs(rem) - 1, cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
               chain2_stage<8>(c, in);
             }
           });
+      first = false;
       chain2_finish<8>(c, has_next);
       pending = true;
-      pend_slot = slot[k];
+      pend_slot = S.slot[k][threadIdx.x];
     }
   }
   drain();

@@ -393,3 +393,39 @@ def test_decode_backward_vs_reference_autograd(model, golden_dir, dev, mode):
     f2, _, _ = vol.query(vol.active_coordinates)
     assert torch.equal(f2, vol.features.detach())
     config.set_mlp_mode("fp32")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc16"])
+def test_arkit_shape_stream_vs_oracle(model, tcnn_params, dev, mode):
+    """BASELINE.json configs[4] shape: 256x192 depth, 2 cm voxels, 10 % invalidated pixels -- the CUDA path
+    against the numpy oracle on the same seeded frames (no golden file: the oracle itself is pinned by
+    tests/test_oracle_golden.py).  ids / weights exact; features and SDF within the mode's tolerance."""
+    from bnv_fusion_b200 import config
+    config.set_mlp_mode(mode)
+    spec = synth.stream_spec("arkit")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vol = _volume(spec, dev, pool_capacity=1 << 18)
+    assert tuple(int(v) for v in vol._n_xyz_host) == tuple(int(v) for v in grid.n_xyz)
+    vm = O.VoxelMap(grid)
+    for fi in range(3):
+        d, K, T = synth.make_frame(spec, fi, seed=5)
+        model.fuse_depth_frame(vol, _depth_to_dev(d, dev), K, T, spec.max_depth)
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        feats, counts, flat, coords, _, _ = O.encode_pointcloud(O.backproject(depth, mask, K, T), grid,
+                                                                tcnn_params["encoder"], 8)
+        O.integrate(vm, flat, feats, counts)
+    vol.check_status()
+    flat, feats, w, h = _map_sorted(vol)
+    rflat = np.sort(np.fromiter(vm.index.keys(), dtype=np.int64))
+    assert len(flat) > 5000 and np.array_equal(flat, rflat)
+    rfeats, rw, _, _ = vm.query(flat)
+    np.testing.assert_allclose(w, rw, atol=1e-6, rtol=0)
+    np.testing.assert_allclose(feats, rfeats, atol=FEAT_ATOL if mode == "fp32" else 5e-3, rtol=0)
+    coords = vol.to_tensor()[0]
+    vol.weights += 8.0
+    vm.weights[: len(vm)] += 8.0
+    q = O.meshlize_samples(coords[:1500].cpu().numpy())
+    sdf = vol.decode_pts(torch.from_numpy(q).to(dev)[None], model.nerf, None, is_coords=True)[0, :, :, 0].cpu().numpy()
+    ref = O.decode_pts(vm, q.reshape(-1, 3), tcnn_params["decoder"], 8).reshape(-1, 27)
+    assert np.abs(sdf - ref).max() <= (SDF_ATOL_FP32 * 2 if mode == "fp32" else SDF_ATOL), np.abs(sdf - ref).max()
+    assert (ref != np.float32(spec.voxel_size)).mean() > 0.3          # blended values, not the fallback

@@ -140,6 +140,54 @@ __global__ void k_latency_elect(int n_mma, int reps, long long* out) {
   teardown(sh);
 }
 
+// F: where do the ~200 cycles of the issue path go?  timestamps around elect / MMAs / commit / wake
+__device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
+template <int N, int NMMA>
+__global__ void k_dissect(int reps, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  Sh& sh = *reinterpret_cast<Sh*>(smem);
+  uint8_t* w = smem + 1024;
+  setup(sh, w);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t base = __shfl_sync(0xffffffffu, sh.tmem, 0);
+  const uint32_t lbo = (N / 8) * 128;
+  const uint32_t wa = smem_u32(w);
+  uint32_t par = 0;
+  long long a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+  for (int r = 0; r < reps; ++r) {
+    __syncthreads();
+    const long long t0 = clk();
+    if (warp == 0) {
+      if (elect_one()) {
+        const long long t1 = clk();
+#pragma unroll
+        for (int kk = 0; kk < NMMA; ++kk)
+          umma_ts_f16(base, base + 448 + (kk & 3) * 8, smem_desc_kmajor(wa + (kk & 3) * 2 * lbo, lbo, 128), idesc_f16_m128(N), kk > 0);
+        const long long t2 = clk();
+        umma_commit(&sh.bar[0]);
+        const long long t3 = clk();
+        a1 += t1 - t0; a2 += t2 - t0; a3 += t3 - t0;
+      }
+    }
+    mbar_wait(&sh.bar[0], par);
+    tc_fence_after();
+    if (threadIdx.x == 32) a4 += clk() - t0;
+    par ^= 1;
+    __syncthreads();
+  }
+  // the elected lane is lane 0 in practice; report from whoever holds non-zero sums
+  if (a3 != 0) { out[0] = a1; out[1] = a2; out[2] = a3; }
+  if (threadIdx.x == 32) out[3] = a4;
+  teardown(sh);
+}
+template <int N, int NMMA> void run_dissect(long long* d, long long* h) {
+  cudaFuncSetAttribute(k_dissect<N, NMMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
+  k_dissect<N, NMMA><<<1, 128, 40000>>>(200, d);
+  cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
+  printf("F: N=%2d, %d MMAs (unrolled): elect done +%.0f, MMAs issued +%.0f, commit issued +%.0f, other warp awake +%.0f cyc\n", N, NMMA,
+         h[0] / 200.0, h[1] / 200.0, h[2] / 200.0, h[3] / 200.0);
+}
+
 template <int N, int NACC> void run_indep(long long* d, long long* h) {
   cudaFuncSetAttribute(k_indep<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
   const int reps = 256;
@@ -177,6 +225,7 @@ template <int N> void run_elect(long long* d, long long* h) {
 int main() {
   long long *d, h[8];
   cudaMalloc(&d, 64);
+  run_dissect<64, 1>(d, h); run_dissect<64, 2>(d, h); run_dissect<64, 4>(d, h); run_dissect<64, 6>(d, h); run_dissect<16, 4>(d, h);
   run_elect<64>(d, h); run_elect<16>(d, h);
   run_indep<64, 1>(d, h); run_indep<64, 2>(d, h); run_indep<64, 4>(d, h);
   run_indep<16, 1>(d, h); run_indep<16, 2>(d, h); run_indep<16, 4>(d, h);
