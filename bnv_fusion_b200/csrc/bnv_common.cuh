@@ -113,6 +113,7 @@ struct bnv_map {
   int32_t* flags;
   int32_t* scan;
   // dense back-projection staging for bnv_backproject
+  double* zlut;         // [65536] (double)d / 1000.0 for every uint16 millimetre depth (load_depth, common.py:93)
   float* bp_pts;
   int32_t* bp_flags;
   int32_t* bp_scan;

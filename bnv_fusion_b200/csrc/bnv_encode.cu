@@ -440,6 +440,7 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   int rc = make_camera(src.cam, H, W, K, T, max_depth);
   if (rc) return rc;
   src.depth = depth;
+  src.zlut = map->zlut;
   cudaStream_t s = (cudaStream_t)stream;
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
   rc = launch_encode(map, src, true, (int64_t)H * W, enc, mode, s);

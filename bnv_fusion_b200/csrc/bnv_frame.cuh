@@ -81,11 +81,106 @@ __device__ __forceinline__ bool backproject_pixel(const uint16_t* __restrict__ d
   return true;
 }
 
+// Same arithmetic with the three kinds of float64 divisions hoisted out of the per-pixel path (bit-identical:
+// every quotient is produced by the same correctly-rounded division, only once instead of per use):
+//   zlut[d]  = (double)d / 1000.0            for every uint16 depth value   (device table, built at map creation)
+//   ax[u]    = ((double)u - cx) / fx         for every image column         (per CTA, shared memory)
+//   ay[v]    = ((double)v - cy) / fy         for every image row
+// 30 float64 divisions per pixel -> 3 (the normal's normalisation).
+__device__ __forceinline__ void build_ratio_tables(const Camera& cam, double* __restrict__ ax, double* __restrict__ ay) {
+  const double fx = (double)cam.fx, fy = (double)cam.fy, cx = (double)cam.cx, cy = (double)cam.cy;
+  for (int i = threadIdx.x; i < cam.W; i += blockDim.x) ax[i] = __ddiv_rn(__dsub_rn((double)i, cx), fx);
+  for (int i = threadIdx.x; i < cam.H; i += blockDim.x) ay[i] = __ddiv_rn(__dsub_rn((double)i, cy), fy);
+}
+
+// the nine raw uint16 depths of the 3x3 neighbourhood (replicate padding), row-major; issued as
+// independent loads so that a caller can prefetch them a tile ahead
+__device__ __forceinline__ void load_depth9(const uint16_t* __restrict__ depth, const Camera& cam, int u, int v,
+                                            uint32_t (&raw)[9]) {
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int uu = min(max(u + dx, 0), cam.W - 1), vv = min(max(v + dy, 0), cam.H - 1);
+      raw[(dy + 1) * 3 + dx + 1] = __ldg(depth + (size_t)vv * cam.W + uu);
+    }
+}
+
+__device__ __forceinline__ bool backproject_raw_lut(const uint32_t (&raw)[9], const Camera& cam,
+                                                    const double* __restrict__ zlut, const double* __restrict__ ax,
+                                                    const double* __restrict__ ay, int u, int v, float (&out)[6]) {
+  auto z_of = [&](uint32_t d) {
+    const double z = __ldg(zlut + d);
+    return (z > 0.0 && z < cam.max_depth) ? z : 0.0;
+  };
+  const double zc = z_of(raw[4]);
+  if (!(zc > 0.0)) return false;
+  double X[3][3], Y[3][3], Z[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int uu = min(max(u + dx, 0), cam.W - 1), vv = min(max(v + dy, 0), cam.H - 1);
+      const double z = (dx == 0 && dy == 0) ? zc : z_of(raw[(dy + 1) * 3 + dx + 1]);
+      X[dy + 1][dx + 1] = __dmul_rn(ax[uu], z);
+      Y[dy + 1][dx + 1] = __dmul_rn(ay[vv], z);
+      Z[dy + 1][dx + 1] = z;
+    }
+  const double e = 0.125;
+  auto sobx = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[1][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[1][2]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  auto soby = [&](double (&P)[3][3]) {
+    double a = __dmul_rn(-e, P[0][0]);
+    a = __dadd_rn(a, __dmul_rn(-2 * e, P[0][1]));
+    a = __dadd_rn(a, __dmul_rn(-e, P[0][2]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][0]));
+    a = __dadd_rn(a, __dmul_rn(2 * e, P[2][1]));
+    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    return a;
+  };
+  const double gx0 = sobx(X), gx1 = sobx(Y), gx2 = sobx(Z);
+  const double gy0 = soby(X), gy1 = soby(Y), gy2 = soby(Z);
+  double n0 = __dsub_rn(__dmul_rn(gx1, gy2), __dmul_rn(gx2, gy1));
+  double n1 = __dsub_rn(__dmul_rn(gx2, gy0), __dmul_rn(gx0, gy2));
+  double n2 = __dsub_rn(__dmul_rn(gx0, gy1), __dmul_rn(gx1, gy0));
+  const double nn = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2)));
+  const double den = fmax(nn, 1e-12);
+  n0 = __ddiv_rn(n0, den); n1 = __ddiv_rn(n1, den); n2 = __ddiv_rn(n2, den);
+  const double xc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)u, cam.cx), cam.fx), zc);
+  const double yc = __dmul_rn((double)__fdiv_rn(__fsub_rn((float)v, cam.cy), cam.fy), zc);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double t0 = (double)cam.T[r * 4 + 0], t1 = (double)cam.T[r * 4 + 1], t2 = (double)cam.T[r * 4 + 2],
+                 t3 = (double)cam.T[r * 4 + 3];
+    const double p = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(xc, t0), __dmul_rn(yc, t1)), __dmul_rn(zc, t2)), t3);
+    const double q = __dadd_rn(__dadd_rn(__dmul_rn(n0, t0), __dmul_rn(n1, t1)), __dmul_rn(n2, t2));
+    out[r] = (float)p;
+    out[3 + r] = (float)q;
+  }
+  return true;
+}
+
+__device__ __forceinline__ bool backproject_pixel_lut(const uint16_t* __restrict__ depth, const Camera& cam,
+                                                      const double* __restrict__ zlut, const double* __restrict__ ax,
+                                                      const double* __restrict__ ay, int u, int v, float (&out)[6]) {
+  uint32_t raw[9];
+  load_depth9(depth, cam, u, v, raw);
+  return backproject_raw_lut(raw, cam, zlut, ax, ay, u, v, out);
+}
+
 struct EncSrc {
   const uint16_t* depth;   // FROM_DEPTH
   Camera cam;
   const float* pts6;       // !FROM_DEPTH
   int64_t n_points;
+  const double* zlut;      // FROM_DEPTH: millimetres -> metres table (bnv_map::zlut)
 };
 
 // split form of scatter_row: claim the voxel's scratch row first (the CAS round trip can then overlap

@@ -160,6 +160,12 @@ __global__ void count_optim_apply_kernel(int32_t* __restrict__ flags, float* __r
   }
 }
 
+// millimetre depth -> metric depth exactly as load_depth computes it (float64 division, src/utils/common.py:93)
+__global__ void zlut_kernel(double* __restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 65536) z[i] = __ddiv_rn((double)i, 1000.0);
+}
+
 // upsert the halo records of the other ranks that this rank needs: 8 lanes per record
 __global__ void insert_halo_kernel(MapDev m, const int32_t* __restrict__ gathered, int world, int64_t cap) {
   const int64_t stride_words = 10 + cap * 10;
@@ -284,6 +290,7 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   alloc((void**)&m->sort_vals_out, (size_t)d.fcap * 4);
   alloc((void**)&m->flags, (size_t)aux * 4);
   alloc((void**)&m->scan, (size_t)aux * 4);
+  alloc((void**)&m->zlut, 65536 * sizeof(double));
   alloc((void**)&m->bp_pts, (size_t)max_points * 6 * 4);
   alloc((void**)&m->bp_flags, (size_t)max_points * 4);
   alloc((void**)&m->bp_scan, (size_t)max_points * 4);
@@ -307,6 +314,8 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   BNV_CUDA(cudaMemsetAsync(m->stats, 0, 64, 0));
   rc = fill_i32(d.ftable, g.n_vox, kEmpty, 0);
   if (rc != BNV_OK) return rc;
+  zlut_kernel<<<256, 256>>>(m->zlut);
+  BNV_LAUNCH_CHECK("zlut_kernel");
   BNV_CUDA(cudaStreamSynchronize(0));
   return BNV_OK;
 }
@@ -317,7 +326,7 @@ int bnv_map_destroy(bnv_map_t* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.fcnt,
                   d.touched, d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
-                  m->sort_vals_out, m->flags, m->scan, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
+                  m->sort_vals_out, m->flags, m->scan, m->zlut, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);

@@ -141,6 +141,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
   RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5;
   const GeomDev& g = m.g;
+  // (u - cx) / fx and (v - cy) / fy in float64 for every column / row, once per CTA (bnv_frame.cuh)
+  double* s_ax = reinterpret_cast<double*>(weights_smem(smem) + ((w_bytes + 127) / 128) * 128);
+  double* s_ay = s_ax + (FROM_DEPTH ? src.cam.W : 0);
+  if (FROM_DEPTH) {
+    build_ratio_tables(src.cam, s_ax, s_ay);
+    __syncthreads();
+  }
   const int64_t n_units = ((n_threads + 127) / 128) * 8;
   const int64_t chain = (int64_t)blockIdx.x * kNWG + wg, n_chains = (int64_t)gridDim.x * kNWG;
   const int64_t u_end = n_units * (chain + 1) / n_chains;
@@ -170,7 +177,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     bool valid = false;
     if (FROM_DEPTH) {
       if (idx < n_threads)
-        valid = backproject_pixel(src.depth, src.cam, (int)(idx % src.cam.W), (int)(idx / src.cam.W), p);
+        valid = backproject_pixel_lut(src.depth, src.cam, src.zlut, s_ax, s_ay, (int)(idx % src.cam.W),
+                                      (int)(idx / src.cam.W), p);
     } else if (idx < n_threads) {
       valid = true;
 #pragma unroll
@@ -309,12 +317,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
 }
 
 // ---- fused decode -----------------------------------------------------------------------------------
-struct AxisPre {       // one axis of a query, floor (s = 0) and ceil (s = 1) flavours
-  uint32_t w_ls[2];    // fp16x2 {l, sin l}
-  uint32_t w_c1[2];    // fp16x2 {cos l, 1}
-  float t[2];          // 1 - |l|
-  int32_t tab[2];      // voxel index * table stride of this axis, or INT_MIN when outside the grid
-  int32_t ts[2];       // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
+// Per-query state lives in shared memory ([word][thread], conflict-free, thread-private): everything that
+// depends on one axis only exists in a floor (s = 0) and a ceil (s = 1) flavour computed once per query,
+// a corner row is then 4 gathered words + 6 selected words + 6 constants.  Keeping it out of the register
+// file leaves room for the 96 transient registers of the hidden-layer epilogue (no spills) and lets the
+// 8-corner loop stay rolled (8x less code, no instruction-cache misses).
+struct DecState {
+  uint32_t w_ls[3][2][kThreads];   // fp16x2 {l, sin l}
+  uint32_t w_c1[3][2][kThreads];   // fp16x2 {cos l, 1}
+  float t[3][2][kThreads];         // 1 - |l|
+  int32_t ts[3][2][kThreads];      // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
+  int32_t slot[8][kThreads];       // table lookup of corner k (_query_tensor)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint4* __restrict__ packed,
@@ -322,10 +335,35 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
   RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
-  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
+  DecState& Q = *reinterpret_cast<DecState*>(weights_smem(smem) + ((w_bytes + 127) / 128) * 128);
+  const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
   const GeomDev& g = m.g;
   constexpr int32_t kOut = INT_MIN;
+  const bool has_prior = a.tsdf != nullptr;
+  auto weight_of = [&](int k) {                                                          // D2, corner k
+    return __fmul_rn(__fmul_rn(Q.t[0][corner_sx(k)][tid], Q.t[1][corner_sy(k)][tid]), Q.t[2][corner_sz(k)][tid]);
+  };
+  auto prior_of = [&](int k) {                                                           // D6, corner k
+    const int32_t px = Q.ts[0][corner_sx(k)][tid], py = Q.ts[1][corner_sy(k)][tid], pz = Q.ts[2][corner_sz(k)][tid];
+    return (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
+  };
+  auto gather = [&](int k, uint4& f, float& w) {                                         // D3
+    f = make_uint4(0, 0, 0, 0);
+    w = 0.f;
+    const int32_t s = Q.slot[k][tid];
+    if (s >= 0 && s < a.n_rows) {
+      f = __ldg(packed + s);
+      w = __ldg(a.weights_rows + s);
+    }
+  };
+  auto stage_corner = [&](int k, const uint4& f) {
+    const int sx = corner_sx(k), sy = corner_sy(k), sz = corner_sz(k);
+    const uint32_t in[16] = {f.x, f.y, f.z, f.w,
+                             Q.w_ls[0][sx][tid], Q.w_c1[0][sx][tid], Q.w_ls[1][sy][tid], Q.w_c1[1][sy][tid],
+                             Q.w_ls[2][sz][tid], Q.w_c1[2][sz][tid], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+    chain2_stage<16>(c, in);
+  };
   // the query whose last corner is still in D_out
   bool pending = false, p_live = false;
   int64_t p_q = 0;
@@ -335,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
       float y[1];
       chain2_output<1>(c, y);
       p_sdf = __fadd_rn(p_sdf, __fmul_rn(__fmul_rn(y[0], g.vs), p_wn));                   // D4, D5 (corner 7)
-      if (a.tsdf) p_dsum = __fadd_rn(p_dsum, __fmul_rn(p_dl, p_wn));                     // D6
+      if (has_prior) p_dsum = __fadd_rn(p_dsum, __fmul_rn(p_dl, p_wn));                  // D6
       if (p_live) {
         bool mask;
         a.out_sdf[p_q] = finish_blend(p_sdf, p_dsum, p_minw, a, g.vs, &mask);
@@ -350,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     float cq[3] = {0.f, 0.f, 0.f};
     if (live) query_coords(m, a, q, cq);
     // ---- once per query: everything that depends on one axis only ---------------------------------
-    AxisPre ax[3];
+    int32_t tab[3][2];                // voxel index * table stride of this axis, or INT_MIN when outside the grid
     const int32_t tstride[3] = {g.nyz, g.n[2], 1};
     const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
 #pragma unroll
@@ -361,13 +399,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
         const float l = __fsub_rn(cq[d], nbv[s]);                                        // D1
         float sn, cs;
         __sincosf(l, &sn, &cs);                                                          // |l| <= 1
-        ax[d].w_ls[s] = pack_f16x2(l, sn);
-        ax[d].w_c1[s] = pack_f16x2(cs, 1.0f);
-        ax[d].t[s] = __fsub_rn(1.f, fabsf(l));
+        Q.w_ls[d][s][tid] = pack_f16x2(l, sn);
+        Q.w_c1[d][s][tid] = pack_f16x2(cs, 1.0f);
+        Q.t[d][s][tid] = __fsub_rn(1.f, fabsf(l));
         const int iv = (int)nbv[s];
-        ax[d].tab[s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
-        ax[d].ts[s] = kOut;
-        if (a.tsdf) {                                                                    // grid_sample(nearest), D6
+        tab[d][s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
+        int32_t ts = kOut;
+        if (has_prior) {                                                                 // grid_sample(nearest), D6
           float t = __fdiv_rn(nbv[s], a.nm1[d]);
           t = __fmul_rn(t, 2.f);
           t = __fsub_rn(t, 1.f);
@@ -375,82 +413,58 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
           t = __fmul_rn(t, 0.5f);
           t = __fmul_rn(t, a.tm1[d]);
           const float rr = nearbyintf(t);
-          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ax[d].ts[s] = (int)rr * pstride[d];
+          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ts = (int)rr * pstride[d];
         }
+        Q.ts[d][s][tid] = ts;
       }
     }
     float wsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float w = __fmul_rn(__fmul_rn(ax[0].t[corner_sx(k)], ax[1].t[corner_sy(k)]), ax[2].t[corner_sz(k)]);
+      const float w = weight_of(k);
       wsum = k == 0 ? w : __fadd_rn(wsum, w);                                            // D2 normaliser
     }
     // ---- 8 independent table lookups in flight (_query_tensor, D3) ---------------------------------
-    int32_t slot[8];
+    int32_t slot0 = kEmpty;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int32_t tx = ax[0].tab[corner_sx(k)], ty = ax[1].tab[corner_sy(k)], tz = ax[2].tab[corner_sz(k)];
-      slot[k] = kEmpty;
-      if (tx != kOut && ty != kOut && tz != kOut) slot[k] = __ldg(m.table + ((int64_t)tx + ty + tz));
+      const int32_t tx = tab[0][corner_sx(k)], ty = tab[1][corner_sy(k)], tz = tab[2][corner_sz(k)];
+      int32_t sl = kEmpty;
+      if (tx != kOut && ty != kOut && tz != kOut) sl = __ldg(m.table + ((int64_t)tx + ty + tz));
+      Q.slot[k][tid] = sl;
+      if (k == 0) slot0 = sl;
     }
     uint4 f_nxt = make_uint4(0, 0, 0, 0);
-    float w_nxt = 0.f, w_cur = 0.f;
-    if (slot[0] >= 0 && slot[0] < a.n_rows) {
-      f_nxt = __ldg(packed + slot[0]);
-      w_nxt = __ldg(a.weights_rows + slot[0]);
+    float w_nxt = 0.f;
+    if (slot0 >= 0 && slot0 < a.n_rows) {
+      f_nxt = __ldg(packed + slot0);
+      w_nxt = __ldg(a.weights_rows + slot0);
     }
     // the previous query's last corner has been in flight during all of the above
     drain();
     float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
-    {
-      const uint32_t in[16] = {f_nxt.x, f_nxt.y, f_nxt.z, f_nxt.w,
-                               ax[0].w_ls[0], ax[0].w_c1[0], ax[1].w_ls[0], ax[1].w_c1[0],
-                               ax[2].w_ls[0], ax[2].w_c1[0], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
-      chain2_stage<16>(c, in);
-      chain2_begin<16>(c);
-      w_cur = w_nxt;
-    }
-#pragma unroll
+    stage_corner(0, f_nxt);
+    chain2_begin<16>(c);
+    float w_cur = w_nxt;
+#pragma unroll 1
     for (int k = 0; k < 8; ++k) {
       minw = fminf(minw, w_cur);                                                         // D3
       chain2_hidden<16>(
           c,
           [&]() {
             // shadow of the second layer: issue the next corner's gather, blend the previous corner
-            if (k < 7) {
-              f_nxt = make_uint4(0, 0, 0, 0);
-              w_nxt = 0.f;
-              const int32_t s = slot[k < 7 ? k + 1 : 7];
-              if (s >= 0 && s < a.n_rows) {
-                f_nxt = __ldg(packed + s);
-                w_nxt = __ldg(a.weights_rows + s);
-              }
-            }
+            if (k < 7) gather(k + 1, f_nxt, w_nxt);
             if (k > 0) {
-              const int kp = k > 0 ? k - 1 : 0;
               float y[1];
               chain2_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
-              const float wk = __fmul_rn(__fmul_rn(ax[0].t[corner_sx(kp)], ax[1].t[corner_sy(kp)]), ax[2].t[corner_sz(kp)]);
-              const float wn = __fdiv_rn(wk, wsum);                                      // D2
+              const float wn = __fdiv_rn(weight_of(k - 1), wsum);                        // D2
               sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                // D4, D5
-              if (a.tsdf) {
-                const int32_t px = ax[0].ts[corner_sx(kp)], py = ax[1].ts[corner_sy(kp)], pz = ax[2].ts[corner_sz(kp)];
-                const float dl = (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
-                dsum = __fadd_rn(dsum, __fmul_rn(dl, wn));                               // D6
-              }
+              if (has_prior) dsum = __fadd_rn(dsum, __fmul_rn(prior_of(k - 1), wn));     // D6
             }
           },
           [&]() {
             // shadow of the third layer: the gather has landed -> stage the next corner's row
-            if (k < 7) {
-              const int kn = k < 7 ? k + 1 : 7;
-              const uint32_t in[16] = {f_nxt.x, f_nxt.y, f_nxt.z, f_nxt.w,
-                                       ax[0].w_ls[corner_sx(kn)], ax[0].w_c1[corner_sx(kn)],
-                                       ax[1].w_ls[corner_sy(kn)], ax[1].w_c1[corner_sy(kn)],
-                                       ax[2].w_ls[corner_sz(kn)], ax[2].w_c1[corner_sz(kn)],
-                                       kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
-              chain2_stage<16>(c, in);
-            }
+            if (k < 7) stage_corner(k + 1, f_nxt);
           });
       chain2_finish<16>(c, k < 7);
       w_cur = w_nxt;
@@ -462,12 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     p_sdf = sdf;
     p_dsum = dsum;
     p_minw = minw;
-    p_wn = __fdiv_rn(__fmul_rn(__fmul_rn(ax[0].t[1], ax[1].t[1]), ax[2].t[1]), wsum);
-    p_dl = 0.f;
-    if (a.tsdf) {
-      const int32_t px = ax[0].ts[1], py = ax[1].ts[1], pz = ax[2].ts[1];
-      if (px != kOut && py != kOut && pz != kOut) p_dl = __ldg(a.tsdf + ((int64_t)px + py + pz));
-    }
+    p_wn = __fdiv_rn(weight_of(7), wsum);
+    p_dl = has_prior ? prior_of(7) : 0.f;
   }
   drain();
   tc_teardown2<kNWG>(S.sh);
@@ -575,7 +585,10 @@ int bnv_internal_encode_chain(bnv_map_t* map, const void* srcp, int from_depth, 
   const EncSrc& src = *reinterpret_cast<const EncSrc*>(srcp);
   const char* e = getenv("BNV_DEBUG_ENCODE");     // profiling experiments only
   const int dbg = e ? atoi(e) : 0;
-  const size_t smem = smem_bytes(enc->in_pad);
+  const size_t tables = from_depth ? (size_t)(src.cam.W + src.cam.H) * 8 : 0;      // float64 ratio tables of the back-projection
+  // weights (padded to 128 B) + the two float64 ratio tables of the back-projection
+  const size_t smem = ((smem_bytes(enc->in_pad) + 127) / 128) * 128 + tables;
+  if (smem > 200 * 1024) { set_error("encode: image of %d x %d is too large for the shared-memory ratio tables", src.cam.W, src.cam.H); return BNV_E_UNSUPPORTED; }
   const int grid = grid_for(((n_threads + 127) / 128) * 8);        // units = (tile, corner)
   if (from_depth) {
     int rc = set_smem(encode_tc_kernel<true>, smem);
@@ -593,7 +606,7 @@ int bnv_internal_encode_chain(bnv_map_t* map, const void* srcp, int from_depth, 
 }
 
 int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
-  const size_t smem = smem_bytes(dec->in_pad);
+  const size_t smem = ((smem_bytes(dec->in_pad) + 127) / 128) * 128 + sizeof(DecState);
   int rc = set_smem(decode_tc_kernel, smem);
   if (rc) return rc;
   decode_tc_kernel<<<grid_for((a.n_queries + 127) / 128), kThreads, smem, s>>>(
