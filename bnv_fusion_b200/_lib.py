@@ -60,6 +60,7 @@ SIGNATURES = {
     "bnv_backproject": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, _P, _P]),
     "bnv_encode_points": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "bnv_integrate": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "bnv_fuse_frame_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_fuse_frame": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_fuse_points": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_decode_sdf": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

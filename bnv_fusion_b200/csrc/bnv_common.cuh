@@ -113,6 +113,14 @@ struct bnv_map {
   int32_t* flags;
   int32_t* scan;
   // dense back-projection staging for bnv_backproject
+  // bnv_fuse_frame_host: two device staging buffers [max_points] uint16, a copy stream for the prefetch hint
+  uint16_t* depth_stage[2];
+  cudaStream_t copy_stream;
+  cudaEvent_t stage_ready[2], stage_free[2];
+  const void* prefetched;  // host pointer whose copy into depth_stage[stage_next] is in flight / done
+  size_t prefetched_bytes;
+  int stage_next;
+  int64_t* user_stats;   // device int64[4] frame statistics of bnv_fuse_frame_host
   double* zlut;         // [65536] (double)d / 1000.0 for every uint16 millimetre depth (load_depth, common.py:93)
   float* bp_pts;
   int32_t* bp_flags;

@@ -451,6 +451,49 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   return rc;
 }
 
+int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_host, int H, int W, const float* K, const float* T,
+                        double max_depth, const bnv_mlp_t* enc, int min_pts, int mode, int64_t* frame_stats_host,
+                        const uint16_t* next_depth_host, void* stream) {
+  if (!map || !depth_host || H <= 0 || W <= 0) { set_error("bnv_fuse_frame_host: bad argument"); return BNV_E_ARG; }
+  if ((int64_t)H * W > map->max_points) {
+    set_error("bnv_fuse_frame_host: %d x %d pixels exceed the map's max_points %lld", H, W, (long long)map->max_points);
+    return BNV_E_CAPACITY;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)H * W * 2;
+  if (!map->copy_stream) {                       // first use: copy stream + buffer events
+    BNV_CUDA(cudaStreamCreateWithFlags(&map->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_ready[i], cudaEventDisableTiming));
+      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_free[i], cudaEventDisableTiming));
+      BNV_CUDA(cudaEventRecord(map->stage_free[i], s));
+    }
+  }
+  const int cur = map->stage_next;
+  if (map->prefetched == depth_host && map->prefetched_bytes == bytes) {
+    BNV_CUDA(cudaStreamWaitEvent(s, map->stage_ready[cur], 0));        // hinted at the previous call: copy in flight / done
+  } else {
+    BNV_CUDA(cudaMemcpyAsync(map->depth_stage[cur], depth_host, bytes, cudaMemcpyHostToDevice, s));
+  }
+  int rc = bnv_fuse_frame(map, map->depth_stage[cur], H, W, K, T, max_depth, enc, min_pts, mode,
+                          frame_stats_host ? map->user_stats : nullptr, nullptr, stream);
+  if (rc) return rc;
+  if (frame_stats_host)
+    BNV_CUDA(cudaMemcpyAsync(frame_stats_host, map->user_stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  BNV_CUDA(cudaEventRecord(map->stage_free[cur], s));                  // this staging buffer's readers are done
+  map->prefetched = nullptr;
+  map->stage_next = cur ^ 1;
+  if (next_depth_host) {
+    const int nxt = cur ^ 1;
+    BNV_CUDA(cudaStreamWaitEvent(map->copy_stream, map->stage_free[nxt], 0));
+    BNV_CUDA(cudaMemcpyAsync(map->depth_stage[nxt], next_depth_host, bytes, cudaMemcpyHostToDevice, map->copy_stream));
+    BNV_CUDA(cudaEventRecord(map->stage_ready[nxt], map->copy_stream));
+    map->prefetched = next_depth_host;
+    map->prefetched_bytes = bytes;
+  }
+  return BNV_OK;
+}
+
 int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,
                     int mode, int64_t* frame_stats, float* navg, void* stream) {
   if (!map || n_points < 0 || (n_points > 0 && !pts6)) { set_error("bnv_fuse_points: bad argument"); return BNV_E_ARG; }

@@ -291,6 +291,9 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   alloc((void**)&m->flags, (size_t)aux * 4);
   alloc((void**)&m->scan, (size_t)aux * 4);
   alloc((void**)&m->zlut, 65536 * sizeof(double));
+  alloc((void**)&m->depth_stage[0], (size_t)max_points * 2);
+  alloc((void**)&m->depth_stage[1], (size_t)max_points * 2);
+  alloc((void**)&m->user_stats, 4 * 8);
   alloc((void**)&m->bp_pts, (size_t)max_points * 6 * 4);
   alloc((void**)&m->bp_flags, (size_t)max_points * 4);
   alloc((void**)&m->bp_scan, (size_t)max_points * 4);
@@ -326,10 +329,15 @@ int bnv_map_destroy(bnv_map_t* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.fcnt,
                   d.touched, d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
-                  m->sort_vals_out, m->flags, m->scan, m->zlut, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
+                  m->sort_vals_out, m->flags, m->scan, m->zlut, m->depth_stage[0], m->depth_stage[1], m->user_stats, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (m->stage_ready[i]) cudaEventDestroy(m->stage_ready[i]);
+    if (m->stage_free[i]) cudaEventDestroy(m->stage_free[i]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   delete m;
   return BNV_OK;
 }

@@ -272,6 +272,24 @@ class LitFusionPointNet(nn.Module):
                                               int(self.min_pts_in_grid), config.mlp_mode(), _lib.ptr(stats),
                                               _lib.ptr(navg), volume._stream()), "bnv_fuse_frame")
 
+    def fuse_depth_frame_host(self, volume, depth_mm_host, K, T_wc, max_depth=3.0, stats_host=None, next_depth_mm_host=None):
+        """Host-buffer form of `fuse_depth_frame`: depth_mm_host is a (pinned) CPU uint16/int16 [H,W] tensor,
+        stats_host a (pinned) CPU int64[4] tensor or None.  H2D copy, fusion and the D2H of the frame statistics
+        are enqueued on the current stream by ONE library call; synchronise the stream before reading stats_host.
+        next_depth_mm_host (optional, pinned) is the frame the following call will pass: its copy is started on
+        the map's copy stream and overlaps this frame's kernels."""
+        assert not depth_mm_host.is_cuda and depth_mm_host.dtype in (torch.uint16, torch.int16)
+        H, W = depth_mm_host.shape
+        K = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+        T = np.ascontiguousarray(np.asarray(T_wc, np.float32).reshape(16))
+        _lib.check(volume._lib.bnv_fuse_frame_host(volume._handle, C.c_void_p(depth_mm_host.data_ptr()), H, W,
+                                                   _lib.ptr(K), _lib.ptr(T), float(max_depth),
+                                                   self.pointnet_backbone._mlp_handle(), int(self.min_pts_in_grid),
+                                                   config.mlp_mode(),
+                                                   C.c_void_p(stats_host.data_ptr()) if stats_host is not None else None,
+                                                   C.c_void_p(next_depth_mm_host.data_ptr()) if next_depth_mm_host is not None else None,
+                                                   volume._stream()), "bnv_fuse_frame_host")
+
     def fuse_points(self, volume, input_pts, stats=None, navg=None):
         pts = input_pts.reshape(-1, 6).detach().float().contiguous()
         _lib.check(volume._lib.bnv_fuse_points(volume._handle, _lib.ptr(pts), pts.shape[0],

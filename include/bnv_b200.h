@@ -159,6 +159,18 @@ int bnv_integrate(bnv_map_t* map, const int64_t* coords_dev, const float* feats_
 int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth_mm_dev, int H, int W, const float* K_host,
                    const float* T_wc_host, double max_depth, const bnv_mlp_t* enc, int min_pts,
                    int mode, int64_t* frame_stats_dev, float* navg_dev, void* stream);
+/* bnv_fuse_frame with HOST buffers, the shape of the reference's per-frame call (src/run_e2e.py:246-252:
+ * the frame arrives in host memory, `.cuda()` per frame): depth_mm_host [H,W] uint16 (pinned memory for a
+ * truly asynchronous copy) -> H2D into a map-owned staging buffer -> fuse -> D2H of the four frame
+ * statistics into frame_stats_host (nullable, pinned), all enqueued on `stream`; no host sync inside.  The
+ * caller synchronises the stream before reading frame_stats_host or reusing depth_mm_host.
+ * next_depth_mm_host (nullable) is a prefetch hint, the role the reference's DataLoader workers play
+ * (run_e2e.py:217-223): its H2D copy is started on the map's copy stream into the second staging buffer and
+ * overlaps this frame's kernels; the next call that passes the same pointer as depth_mm_host skips its copy.
+ * The hinted buffer must stay valid and unchanged until that next call's work has completed. */
+int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_mm_host, int H, int W, const float* K_host,
+                        const float* T_wc_host, double max_depth, const bnv_mlp_t* enc, int min_pts,
+                        int mode, int64_t* frame_stats_host, const uint16_t* next_depth_mm_host, void* stream);
 /* Same, starting from world-space points (frame['input_pts'], [n,6] fp32). */
 int bnv_fuse_points(bnv_map_t* map, const float* pts6_dev, int64_t n_points, const bnv_mlp_t* enc,
                     int min_pts, int mode, int64_t* frame_stats_dev, float* navg_dev, void* stream);

@@ -429,3 +429,28 @@ def test_arkit_shape_stream_vs_oracle(model, tcnn_params, dev, mode):
     ref = O.decode_pts(vm, q.reshape(-1, 3), tcnn_params["decoder"], 8).reshape(-1, 27)
     assert np.abs(sdf - ref).max() <= (SDF_ATOL_FP32 * 2 if mode == "fp32" else SDF_ATOL), np.abs(sdf - ref).max()
     assert (ref != np.float32(spec.voxel_size)).mean() > 0.3          # blended values, not the fallback
+
+
+def test_host_buffer_call_matches_device_call(model, dev):
+    """bnv_fuse_frame_host (pinned host depth in, frame statistics out to pinned host memory, one call) leaves the
+    map and the statistics of bnv_fuse_frame on a device-resident frame, bit for bit."""
+    spec = synth.stream_spec("parity64")
+    va, vb = _volume(spec, dev, pool_capacity=1 << 16), _volume(spec, dev, pool_capacity=1 << 16)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+    fr = [synth.make_frame(spec, fi, seed=3) for fi in range(6)]
+    hosts = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in fr]
+    for fi in range(6):
+        d, K, T = fr[fi]
+        model.fuse_depth_frame(va, _depth_to_dev(d, dev), K, T, spec.max_depth, stats=stats)
+        # frames 0..2 hint the next frame (prefetched on the copy stream), 3..5 do not (copy on the call's stream)
+        nxt = hosts[fi + 1] if fi < 3 else None
+        model.fuse_depth_frame_host(vb, hosts[fi], K, T, spec.max_depth, stats_host=stats_host, next_depth_mm_host=nxt)
+        torch.cuda.synchronize()
+        assert stats.cpu().tolist() == stats_host.tolist() and int(stats_host[3]) > 0
+    a, b = _map_sorted(va), _map_sorted(vb)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(RuntimeError):       # a frame larger than the map's max_points fails loudly
+        big = torch.zeros((4096, 4096), dtype=torch.int16).pin_memory()
+        model.fuse_depth_frame_host(vb, big, K, T, spec.max_depth)
