@@ -36,6 +36,8 @@ ENC_FLOP_PER_ROW = 2 * (6 * 64 + 64 * 64 + 64 * 64 + 64 * 8)         # 18 176 (S
 DEC_FLOP_PER_QUERY = 8 * 2 * (17 * 64 + 64 * 64 + 64 * 64 + 64 * 1)  # 149 504
 N_FRAMES = 16
 WORKLOAD = "lounge"
+WORKLOAD_DESC = ("lounge 640x480 depth, 1 cm voxels, 512^3 sparse grid, per-frame local fusion "
+                 "(backproject+encode+integrate), pretrained pointnet_tcnn weights")
 
 
 def traffic(kernel):
@@ -144,7 +146,7 @@ def run_reference(args):
         "impl": "reference", "metric": "fusion_frames_per_sec", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (spec.height / sample_rows),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "lounge 640x480 depth, 1 cm voxels, 512^3 sparse grid, per-frame local fusion"},
+        "config": {"workload": WORKLOAD_DESC, "frames": 4, "mlp": "float64 numpy (oracle port)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -379,9 +381,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
             "data": "synthetic",
-            "config": {"workload": "lounge 640x480 depth, 1 cm voxels, 512^3 sparse grid, per-frame local fusion "
-                                   "(backproject+encode+integrate), pretrained pointnet_tcnn weights",
-                       "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
+            "config": {"workload": WORKLOAD_DESC, "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"tile shard over {world} GPUs, 3-D checkerboard of {1 << args.brick_log2}-voxel bricks, one all-gather per frame"},
             "value_warm": 1e3 / warm_ms,

@@ -26,28 +26,47 @@ __global__ void pack_rows_kernel(const float* __restrict__ feats, int64_t n, uin
   out[i] = make_uint4(pack_f16x2(a.x, a.y), pack_f16x2(a.z, a.w), pack_f16x2(b.x, b.y), pack_f16x2(b.z, b.w));
 }
 
-// per sample: 8 corner lookups into G + trilinear blend + mask + prior (rules D1-D6)
+// Per sample: 8 corner lookups into G + trilinear blend + mask + prior (rules D1-D6).  One warp per active
+// voxel, lane s = sample s AND neighbour s of the voxel's 3x3x3 neighbourhood: the 27 table / weight lookups
+// are done once per voxel and handed to the samples by shuffle (every corner of every sample is one of the
+// 27 neighbours), instead of 8 x 27 lookups.  Arithmetic and corner order are those of the per-query kernel.
 __global__ void __launch_bounds__(256) blend_blocks_kernel(MapDev m, DecArgs a, const float* __restrict__ G) {
-  const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (q >= a.n_queries) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t vl = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // voxel of this warp
+  const int64_t n_vox = a.n_queries / 27;
+  if (vl >= n_vox) return;                                                         // warp-uniform
   const GeomDev& g = m.g;
-  const int64_t v = a.first_voxel + q / 27;
-  const int s = (int)(q % 27);
+  const int64_t v = a.first_voxel + vl;
   const int32_t flat0 = m.keys[v];
   const int id[3] = {flat0 / g.nyz, (flat0 % g.nyz) / g.n[2], flat0 % g.n[2]};
-  const int o[3] = {s / 9 - 1, (s / 3) % 3 - 1, s % 3 - 1};     // sample offset / 0.5
-  // per axis, floor (j = 0) and ceil (j = 1) corner: voxel index, l digit (0: -0.5, 1: 0, 2: +0.5), 1 - |l|
-  int nbv[3][2], ld[3][2];
+  const int s = lane < 27 ? lane : 0;
+  const int o[3] = {s / 9 - 1, (s / 3) % 3 - 1, s % 3 - 1};     // sample offset / 0.5 == neighbour offset
+  // ---- as neighbour `lane`: row in G (miss voxel = n_rows) and fusion weight -------------------------------
+  int32_t my_gv = (int32_t)a.n_rows;
+  float my_wt = 0.f;
+  {
+    const int ix = id[0] + o[0], iy = id[1] + o[1], iz = id[2] + o[2];
+    if (lane < 27 && ix >= 0 && iy >= 0 && iz >= 0 && ix < g.n[0] && iy < g.n[1] && iz < g.n[2]) {
+      const int32_t slot = __ldg(m.table + ((int64_t)ix * g.nyz + iy * g.n[2] + iz));
+      if (slot >= 0 && slot < a.n_rows) {
+        my_gv = slot;
+        my_wt = __ldg(a.weights_rows + slot);
+      }
+    }
+  }
+  // ---- as sample `lane` -------------------------------------------------------------------------------------
+  // per axis, floor (j = 0) and ceil (j = 1) corner: neighbour offset, l digit (0: -0.5, 1: 0, 2: +0.5), 1 - |l|
+  int nbo[3][2], ld[3][2];
   float tt[3][2], nbf[3][2];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    nbv[d][0] = o[d] < 0 ? id[d] - 1 : id[d];
-    nbv[d][1] = o[d] > 0 ? id[d] + 1 : id[d];
+    nbo[d][0] = o[d] < 0 ? -1 : 0;
+    nbo[d][1] = o[d] > 0 ? 1 : 0;
     ld[d][0] = o[d] == 0 ? 1 : 2;
     ld[d][1] = o[d] == 0 ? 1 : 0;
     tt[d][0] = tt[d][1] = o[d] == 0 ? 1.0f : 0.5f;
-    nbf[d][0] = (float)nbv[d][0];
-    nbf[d][1] = (float)nbv[d][1];
+    nbf[d][0] = (float)(id[d] + nbo[d][0]);
+    nbf[d][1] = (float)(id[d] + nbo[d][1]);
   }
   constexpr int SX[8] = {0, 1, 0, 0, 1, 1, 0, 1}, SY[8] = {0, 0, 1, 0, 1, 0, 1, 1}, SZ[8] = {0, 0, 0, 1, 0, 1, 1, 1};
   float wsum = 0.f;
@@ -59,18 +78,11 @@ __global__ void __launch_bounds__(256) blend_blocks_kernel(MapDev m, DecArgs a, 
   float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int ix = nbv[0][SX[k]], iy = nbv[1][SY[k]], iz = nbv[2][SZ[k]];
-    int64_t gv = a.n_rows;                                        // miss voxel
-    float wt = 0.f;
-    if (ix >= 0 && iy >= 0 && iz >= 0 && ix < g.n[0] && iy < g.n[1] && iz < g.n[2]) {
-      const int32_t slot = __ldg(m.table + ((int64_t)ix * g.nyz + iy * g.n[2] + iz));
-      if (slot >= 0 && slot < a.n_rows) {
-        gv = slot;
-        wt = __ldg(a.weights_rows + slot);
-      }
-    }
+    const int nb_lane = (nbo[0][SX[k]] + 1) * 9 + (nbo[1][SY[k]] + 1) * 3 + (nbo[2][SZ[k]] + 1);
+    const int32_t gv = __shfl_sync(0xffffffffu, my_gv, nb_lane);
+    const float wt = __shfl_sync(0xffffffffu, my_wt, nb_lane);
     minw = fminf(minw, wt);
-    const float y = __ldg(G + gv * 27 + (ld[0][SX[k]] * 9 + ld[1][SY[k]] * 3 + ld[2][SZ[k]]));
+    const float y = __ldg(G + (int64_t)gv * 27 + (ld[0][SX[k]] * 9 + ld[1][SY[k]] * 3 + ld[2][SZ[k]]));
     const float wn = __fdiv_rn(__fmul_rn(__fmul_rn(tt[0][SX[k]], tt[1][SY[k]]), tt[2][SZ[k]]), wsum);
     sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y, g.vs), wn));
     if (a.tsdf) {
@@ -78,8 +90,10 @@ __global__ void __launch_bounds__(256) blend_blocks_kernel(MapDev m, DecArgs a, 
       dsum = __fadd_rn(dsum, __fmul_rn(tsdf_nearest(a, g, nb), wn));
     }
   }
-  bool mask;
-  a.out_sdf[q] = finish_blend(sdf, dsum, minw, a, g.vs, &mask);
+  if (lane < 27) {
+    bool mask;
+    a.out_sdf[vl * 27 + lane] = finish_blend(sdf, dsum, minw, a, g.vs, &mask);
+  }
 }
 
 }  // namespace tc
@@ -141,7 +155,7 @@ int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_
     }
     int rc = bnv_internal_gtable_chain(map, a.n_rows, dec, s);
     if (rc) return rc;
-    blend_blocks_kernel<<<(unsigned)((a.n_queries + 255) / 256), 256, 0, s>>>(map->d, a, (const float*)map->gtable);
+    blend_blocks_kernel<<<(unsigned)((a.n_queries / 27 + 7) / 8), 256, 0, s>>>(map->d, a, (const float*)map->gtable);   // one warp per voxel
     BNV_LAUNCH_CHECK("blend_blocks_kernel");
     return BNV_OK;
   }
