@@ -416,7 +416,8 @@ def run_b200(args):
                        "path": "bnv_decode_voxel_blocks (meshlize samples): G[voxel][offset] table on the tensor cores + blend",
                        "roofline": {"bound": "tensor", "achieved": exe_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                                     "frac": exe_tflops / pk["tf_sustained"], "algorithmic_tflops": dec_tflops,
-                                    "traffic": traffic("decode_tc_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel"),
+                                    "traffic": ((traffic("gtable_tc_kernel") or 0) + (traffic("blend_blocks_kernel") or 0)) or None
+                                               if config.mlp_mode_name() == "tc16" else traffic("decode_simt_kernel"),
                                     "peak_source": pk["src"],
                                     "note": "achieved = FLOPs executed on the tensor pipe over the time of BOTH kernels (G table + "
                                             "blend): the block path evaluates each distinct (voxel, offset) MLP row once, 27 "
