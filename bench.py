@@ -254,14 +254,13 @@ def run_b200(args):
     warm_ms = e0.elapsed_time(e1) / args.steps
     # ---- end to end through the public API / C ABI with HOST buffers ----------------------------
     # every step: pinned uint16 depth -> H2D -> fuse -> D2H of the frame statistics -> host sync
-    # (bnv_fuse_frame_host, one library call per frame; the tile shard goes through the device-buffer path)
+    # (bnv_fuse_frame_host, one library call per frame; the tile shard adds its boundary exchange on the side stream)
     def step_e2e(i):
         _, K, T = frames[i % N_FRAMES]
-        if shard is not None:
-            step(i, from_host=True)
-            return
-        model.fuse_depth_frame_host(vol, host[i % N_FRAMES], K, T, spec.max_depth, stats_host=stats_host,
-                                    next_depth_mm_host=host[(i + 1) % N_FRAMES])     # prefetch hint
+        target = shard if shard is not None else model
+        args_ = () if shard is not None else (vol,)
+        target.fuse_depth_frame_host(*args_, host[i % N_FRAMES], K, T, spec.max_depth, stats_host=stats_host,
+                                     next_depth_mm_host=host[(i + 1) % N_FRAMES])    # prefetch hint
         torch.cuda.current_stream().synchronize()          # the user reads the frame's result
 
     for i in range(3):
@@ -273,7 +272,7 @@ def run_b200(args):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
-    assert shard is not None or int(stats_host[0]) > 0
+    assert int(stats_host[0]) > 0
     clocks = sampler.stop()
     vol.check_status()
     # ---- reference "local" timer scope: neural fusion + coarse TSDF prior (run_e2e.py:78-109) -----------

@@ -41,7 +41,15 @@ __global__ void __launch_bounds__(256) tsdf_integrate_kernel(float* __restrict__
                                                              const float* __restrict__ rgb, double obs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)nx * ny * nz) return;
-  const int z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((int64_t)nz * ny));
+  int x, y, z;
+  if ((int64_t)nx * ny * nz < (1ll << 31)) {     // 32-bit index arithmetic (the 64-bit divisions were a third of the kernel)
+    const uint32_t i32 = (uint32_t)i, q = i32 / (uint32_t)nz;
+    z = (int)(i32 - q * (uint32_t)nz);
+    x = (int)(q / (uint32_t)ny);
+    y = (int)(q - (uint32_t)x * (uint32_t)ny);
+  } else {
+    z = (int)(i % nz), y = (int)((i / nz) % ny), x = (int)(i / ((int64_t)nz * ny));
+  }
   // vox2world (fusion.py:169-180): float32(origin) + float64(vs) * float32(coord) -> float32
   const float wx = (float)((double)ox + vs * (double)(float)x);
   const float wy = (float)((double)oy + vs * (double)(float)y);

@@ -125,6 +125,15 @@ class TileShardedFusion:
         Integration only ever touches voxels this rank owns, halo copies are only read by decode: the
         all-gather + halo upsert of frame f therefore runs on a side stream, overlapped with the fusion of
         frame f + 1; `synchronize()` (called by the volume's read paths) joins the two streams."""
+        self._fuse(lambda: self.model.fuse_depth_frame(self.volume, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg))
+
+    def fuse_depth_frame_host(self, depth_mm_host, K, T_wc, max_depth=3.0, stats_host=None, next_depth_mm_host=None):
+        """Same from a (pinned) host frame: H2D + fuse + D2H of the statistics in one library call
+        (LitFusionPointNet.fuse_depth_frame_host), then the boundary exchange."""
+        self._fuse(lambda: self.model.fuse_depth_frame_host(self.volume, depth_mm_host, K, T_wc, max_depth,
+                                                            stats_host=stats_host, next_depth_mm_host=next_depth_mm_host))
+
+    def _fuse(self, fuse_call):
         import torch.distributed as dist
         torch = self.torch
         v, lib = self.volume, self._lib
@@ -134,7 +143,7 @@ class TileShardedFusion:
             main.wait_event(self.done[i])
         self._attach(i)
         lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
-        self.model.fuse_depth_frame(v, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg)
+        fuse_call()
         if self.world > 1:
             if not self.overlap:
                 dist.all_gather_into_tensor(self.gathered[i], self.halo[i], group=self.group)   # the one collective
