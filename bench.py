@@ -187,7 +187,7 @@ def run_b200(args):
     shard = None
     if world > 1:
         from bnv_fusion_b200.dist import TileShardedFusion
-        shard = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2)
+        shard = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange)
     H, W = spec.height, spec.width
     host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
     devf = [h.to(dev).view(torch.uint16) for h in host]
@@ -382,7 +382,8 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC, "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"tile shard over {world} GPUs, 3-D checkerboard of {1 << args.brick_log2}-voxel bricks, one all-gather per frame"},
+                       f"tile shard over {world} GPUs, 3-D checkerboard of {1 << args.brick_log2}-voxel bricks, " +
+                       ("one all-gather per frame" if args.exchange == "nccl" else "peer-memory boundary routing")},
             "value_warm": 1e3 / warm_ms,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
                     "d2h_bytes_per_step": 32,
@@ -443,6 +444,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
+                    help="tile shard boundary exchange: one NCCL all-gather per frame (default) or the experimental "
+                         "peer-memory routing (csrc/bnv_p2p.cu)")
     ap.add_argument("--brick-log2", type=int, default=6, help="tile shard: owner bricks of 2^b voxels per side")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -53,6 +53,12 @@ SIGNATURES = {
     "bnv_map_set_halo_buffer": (C.c_int, [_P, _P, _I64]),
     "bnv_map_halo_begin": (C.c_int, [_P, _P]),
     "bnv_map_insert_halo": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
+    "bnv_exchange_create": (C.c_int, [C.POINTER(_P), _P, _I64]),
+    "bnv_exchange_handle": (C.c_int, [_P, _P]),
+    "bnv_exchange_connect": (C.c_int, [_P, _P]),
+    "bnv_exchange_push": (C.c_int, [_P, _P]),
+    "bnv_exchange_join": (C.c_int, [_P, _P]),
+    "bnv_exchange_destroy": (C.c_int, [_P]),
     "bnv_map_query": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P]),
     "bnv_map_insert": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "bnv_map_export": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),

@@ -17,6 +17,7 @@ constexpr double kFixScale = 1073741824.0;  // 2^30: fixed-point scale of the pe
 // latched device-side status bits
 constexpr int kErrCapacity = 1;     // value pool or frame scratch full
 constexpr int kErrRange = 2;        // key outside the grid
+constexpr int kErrExchange = 4;     // peer-memory halo exchange: a peer's frame never arrived (bnv_p2p.cu)
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

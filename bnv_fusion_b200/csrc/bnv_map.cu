@@ -368,6 +368,7 @@ int bnv_map_status(bnv_map_t* m, void* stream) {
   BNV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   if (c[2] & kErrCapacity) { set_error("voxel map capacity exceeded (capacity %d, frame rows %d)", m->d.cap, m->d.fcap); return BNV_E_CAPACITY; }
   if (c[2] & kErrRange) { set_error("voxel key outside the %d x %d x %d grid", m->d.g.n[0], m->d.g.n[1], m->d.g.n[2]); return BNV_E_RANGE; }
+  if (c[2] & kErrExchange) { set_error("peer-memory halo exchange timed out waiting for another rank"); return BNV_E_CUDA; }
   return BNV_OK;
 }
 

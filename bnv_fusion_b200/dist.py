@@ -93,7 +93,8 @@ def select_needed(flat, n_xyz, rank, world, brick_log2):
 class TileShardedFusion:
     """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
 
-    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None, overlap=True):
+    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None, overlap=True,
+                 exchange="nccl"):
         import torch
         from . import _lib
         self.torch, self._lib = torch, _lib
@@ -113,6 +114,25 @@ class TileShardedFusion:
         volume.set_shard(self.rank, self.world, self.brick_log2)
         volume._halo_sync = self.synchronize     # SparseVolume reads (to_tensor, decode) wait for the halo
         self._attach(0)
+        # exchange="p2p": EXPERIMENTAL peer-memory routing (csrc/bnv_p2p.cu, not yet validated on hardware);
+        # the default is the all-gather the north star names
+        self.exchange = exchange
+        self._ex = None
+        if exchange == "p2p" and self.world > 1:
+            import torch.distributed as dist
+            lib = volume._lib
+            ex = C.c_void_p()
+            _lib.check(lib.bnv_exchange_create(C.byref(ex), volume._handle, self.capacity), "bnv_exchange_create")
+            mine = (C.c_ubyte * 64)()
+            _lib.check(lib.bnv_exchange_handle(ex, mine), "bnv_exchange_handle")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine), group=group)
+            blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            _lib.check(lib.bnv_exchange_connect(ex, blob), "bnv_exchange_connect")
+            dist.barrier(group=group)
+            self._ex = ex
+        elif exchange != "nccl":
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
 
     def _attach(self, i):
         v = self.volume
@@ -137,6 +157,11 @@ class TileShardedFusion:
         import torch.distributed as dist
         torch = self.torch
         v, lib = self.volume, self._lib
+        if self._ex is not None:                 # peer-memory exchange: routing + waits live in the library
+            lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
+            fuse_call()
+            lib.check(v._lib.bnv_exchange_push(self._ex, v._stream()), "bnv_exchange_push")
+            return
         i = self.flip
         main = torch.cuda.current_stream(v.device)
         if self.done[i] is not None:             # the exchange two frames ago used this buffer pair
@@ -162,6 +187,9 @@ class TileShardedFusion:
 
     def synchronize(self):
         """the current stream waits for every halo exchange issued so far"""
+        if self._ex is not None:
+            self._lib.check(self.volume._lib.bnv_exchange_join(self._ex, self.volume._stream()), "bnv_exchange_join")
+            return
         main = self.torch.cuda.current_stream(self.volume.device)
         for ev in self.done:
             if ev is not None:
@@ -175,4 +203,8 @@ class TileShardedFusion:
     def detach(self):
         self.synchronize()
         self.volume._halo_sync = None
+        if self._ex is not None:
+            self.torch.cuda.synchronize()
+            self._lib.check(self.volume._lib.bnv_exchange_destroy(self._ex), "bnv_exchange_destroy")
+            self._ex = None
         self._lib.check(self.volume._lib.bnv_map_set_halo_buffer(self.volume._handle, None, 0), "detach halo")

@@ -106,6 +106,21 @@ int bnv_map_halo_begin(bnv_map_t* map, void* stream);
 int bnv_map_insert_halo(bnv_map_t* map, const void* gathered_dev, int world, int64_t capacity_records,
                         void* stream);
 
+/* EXPERIMENTAL peer-memory variant of the halo exchange (csrc/bnv_p2p.cu; not yet validated on hardware, the
+ * all-gather path above is the default): the sender routes each boundary record straight into the inbox of
+ * the ranks that need it (stores over NVLink into cudaIpc-mapped memory), the receiver upserts its inbox on a
+ * side stream once every peer's frame sequence number has arrived.  Usage, one process per GPU:
+ *   bnv_map_set_shard + bnv_map_set_halo_buffer, bnv_exchange_create, bnv_exchange_handle (64 bytes),
+ *   all-gather the handles by any transport, bnv_exchange_connect; then per frame, on every rank:
+ *   bnv_map_halo_begin, bnv_fuse_frame*, bnv_exchange_push; bnv_exchange_join before reading the map. */
+typedef struct bnv_exchange bnv_exchange_t;
+int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_records_per_peer);
+int bnv_exchange_handle(bnv_exchange_t* ex, void* handle64_out_host);
+int bnv_exchange_connect(bnv_exchange_t* ex, const void* handles_host /* [world][64], rank order */);
+int bnv_exchange_push(bnv_exchange_t* ex, void* stream);
+int bnv_exchange_join(bnv_exchange_t* ex, void* stream);
+int bnv_exchange_destroy(bnv_exchange_t* ex);
+
 /* SparseVolume.query (sparse_volume.py:661-695): coords_dev [n,3] int64 -> feats [n,F], weights [n],
  * num_hits [n] (zeros for misses), found [n] uint8 (nullable). */
 int bnv_map_query(bnv_map_t* map, const int64_t* coords_dev, int64_t n, float* feats_dev,

@@ -29,7 +29,7 @@ def _setup(dev):
     return m
 
 
-def _worker(rank, world, port, out_dir, mode):
+def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
     import torch.distributed as dist
     from bnv_fusion_b200 import synth, config
     config.set_mlp_mode(mode)
@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_dir, mode):
     model = _setup(dev)
     spec = synth.stream_spec("lounge")
     vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
-    shard = TileShardedFusion(vol, model, rank, world, brick_log2=4)
+    shard = TileShardedFusion(vol, model, rank, world, brick_log2=4, exchange=exchange)
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     rows = 0
     for fi in range(N_FRAMES):
@@ -62,8 +62,12 @@ def _worker(rank, world, port, out_dir, mode):
     dist.destroy_process_group()
 
 
+EXCHANGES = ["nccl"] + (["p2p"] if os.environ.get("BNV_TEST_P2P") == "1" else [])   # p2p: opt-in until validated
+
+
+@pytest.mark.parametrize("exchange", EXCHANGES)
 @pytest.mark.parametrize("mode", ["fp32", "tc16"])
-def test_two_gpu_tile_shard(tmp_path, mode):
+def test_two_gpu_tile_shard(tmp_path, mode, exchange):
     """fp32 mode (order-independent fixed-point sums): owned + halo values bit-identical to one GPU.
     tc16 mode (fp32 `red.add` partial sums, arrival order differs between runs): same voxels, values to
     summation-order noise."""
@@ -73,7 +77,7 @@ def test_two_gpu_tile_shard(tmp_path, mode):
     from bnv_fusion_b200 import synth, config
     from bnv_fusion_b200.volume import SparseVolume
     world = 2
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path), mode), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path), mode, exchange), nprocs=world, join=True)
     config.set_mlp_mode(mode)
     exact = mode == "fp32"
 
