@@ -1,5 +1,7 @@
-"""Ablation of the tensor-core encode kernel (profiling aid): BNV_DEBUG_ENCODE = 1 no MMA chain,
-2 no feature reductions, 3 no claim + no reductions; plus points-in (no back-projection) vs depth-in."""
+"""Ablation of the tensor-core encode kernel (profiling aid).  BNV_DEBUG_ENCODE is a bit mask: 1 no MMA chain,
+2 no feature reductions, 4 no claims (+ no reductions), 8 whole tiles per chain instead of the (tile, corner)
+split, 16 run-length shuffle aggregation of the reductions; each is timed depth-in and points-in (no
+back-projection).  usage: python tools/encode_experiment.py 0 1 2 4 7 ...   (results: profiles/r1c_umma_microbench2.txt)"""
 import os, sys, json, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 code = r'''
