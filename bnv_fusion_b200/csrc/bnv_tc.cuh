@@ -230,6 +230,36 @@ __device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0,
 constexpr int kInCol = 96;
 constexpr int kOutCol = 112;
 
+// Optional phase timers of the chain (make EXTRA=-DBNV_CHAIN_PROFILE=1, tools/chain_phase_profile.py): thread 0 of
+// every warpgroup accumulates clock64 deltas per phase into a per-translation-unit device array.  With the macro
+// off (default) the hooks expand to nothing.
+#ifndef BNV_CHAIN_PROFILE
+#define BNV_CHAIN_PROFILE 0
+#endif
+#if BNV_CHAIN_PROFILE
+static __device__ unsigned long long g_chain_prof[16];
+__device__ __forceinline__ long long prof_clk() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+  return t;
+}
+#define BNV_PROF_MARK(t) const long long t = ::bnv::tc::prof_clk()
+#define BNV_PROF_ADD(i, t0)                                                                                     \
+  do {                                                                                                          \
+    if ((threadIdx.x & 127) == 0) atomicAdd(&::bnv::tc::g_chain_prof[i], (unsigned long long)(::bnv::tc::prof_clk() - (t0))); \
+  } while (0)
+#define BNV_PROF_COUNT(i)                                                           \
+  do {                                                                              \
+    if ((threadIdx.x & 127) == 0) atomicAdd(&::bnv::tc::g_chain_prof[i], 1ull);     \
+  } while (0)
+#else
+#define BNV_PROF_MARK(t)
+#define BNV_PROF_ADD(i, t0)
+#define BNV_PROF_COUNT(i)
+#endif
+// phase indices: 0 wait L0 | 1 epilogue+issue L1 | 2 shadow1 | 3 wait L1 | 4 epilogue+issue L2 | 5 shadow2 |
+// 6 wait L2 | 7 epilogue 3 | 8 finish (issue L3 + next L0) | 9 per-tile precompute | 10 lifetime | 11 items
+
 // floor (0) / ceil (1) flavour of corner k per axis, get_neighbors' order (src/models/fusion/utils.py:98-167):
 // k: (f,f,f) (c,f,f) (f,c,f) (f,f,c) (c,c,f) (c,f,c) (f,c,c) (c,c,c)
 __host__ __device__ constexpr int corner_sx(int k) { return (0xB2 >> k) & 1; }
@@ -374,24 +404,40 @@ __device__ __forceinline__ void chain2_epilogue(RowChain2& c) {
 template <int INW, class Shadow1, class Shadow2>
 __device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, Shadow2&& shadow2) {
   constexpr int off1 = 2 * INW * 64 * 2, off2 = off1 + 64 * 64 * 2;
+  BNV_PROF_MARK(p0);
   chain2_wait_d(c);
+  BNV_PROF_ADD(0, p0);
+  BNV_PROF_MARK(p1);
   chain2_epilogue(c);
   chain2_sync_issue(c, [&]() {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off1, 0, kACol, kk);
     umma_commit(c.bar_d);
   });
+  BNV_PROF_ADD(1, p1);
+  BNV_PROF_MARK(p2);
   shadow1();
+  BNV_PROF_ADD(2, p2);
+  BNV_PROF_MARK(p3);
   chain2_wait_d(c);
+  BNV_PROF_ADD(3, p3);
+  BNV_PROF_MARK(p4);
   chain2_epilogue(c);
   chain2_sync_issue(c, [&]() {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off2, 0, kACol, kk);
     umma_commit(c.bar_d);
   });
+  BNV_PROF_ADD(4, p4);
+  BNV_PROF_MARK(p5);
   shadow2();
+  BNV_PROF_ADD(5, p5);
+  BNV_PROF_MARK(p6);
   chain2_wait_d(c);
+  BNV_PROF_ADD(6, p6);
+  BNV_PROF_MARK(p7);
   chain2_epilogue(c);
+  BNV_PROF_ADD(7, p7);
 }
 
 // output layer of the current item + (has_next) L0 of the staged next item, interleaved in one burst:
@@ -399,6 +445,7 @@ __device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, S
 template <int INW>
 __device__ __forceinline__ void chain2_finish(RowChain2& c, bool has_next) {
   constexpr int off3 = 2 * INW * 64 * 2 + 2 * 64 * 64 * 2;
+  BNV_PROF_MARK(p8);
   chain2_sync_issue(c, [&]() {
     if (has_next) {
 #pragma unroll
@@ -414,6 +461,8 @@ __device__ __forceinline__ void chain2_finish(RowChain2& c, bool has_next) {
       umma_commit(c.bar_o);
     }
   });
+  BNV_PROF_ADD(8, p8);
+  BNV_PROF_COUNT(11);
 }
 
 // read the NOUT outputs of the item whose chain2_finish was issued last (waits for its output layer)

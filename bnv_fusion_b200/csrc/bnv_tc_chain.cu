@@ -382,7 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
       pending = false;
     }
   };
+  BNV_PROF_MARK(p_life);
   for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
+    BNV_PROF_MARK(p_pre);
     const int64_t q = tile * 128 + r;
     const bool live = q < a.n_queries;
     float cq[3] = {0.f, 0.f, 0.f};
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
     stage_corner(0, f_nxt);
     chain2_begin<16>(c);
+    BNV_PROF_ADD(9, p_pre);
     float w_cur = w_nxt;
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
@@ -480,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     p_dl = has_prior ? prior_of(7) : 0.f;
   }
   drain();
+  BNV_PROF_ADD(10, p_life);
   tc_teardown2<kNWG>(S.sh);
 }
 
@@ -625,3 +629,16 @@ int bnv_internal_gtable_chain(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* d
   BNV_LAUNCH_CHECK("gtable_tc_kernel");
   return BNV_OK;
 }
+
+#if BNV_CHAIN_PROFILE
+// profiling build only: read (and reset) the phase timers of this translation unit's chain kernels
+extern "C" int bnv_debug_chain_profile(unsigned long long* out16, int reset) {
+  BNV_CUDA(cudaDeviceSynchronize());
+  BNV_CUDA(cudaMemcpyFromSymbol(out16, bnv::tc::g_chain_prof, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    BNV_CUDA(cudaMemcpyToSymbol(bnv::tc::g_chain_prof, z, sizeof(z)));
+  }
+  return BNV_OK;
+}
+#endif
