@@ -276,7 +276,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-struct RowChain2 {
+struct RowChain {
   uint32_t t_d, t_a, t_in, t_o;  // this warp's lane base at the slot's D / A_h / A_in / D_out columns
   uint32_t d_slot;               // slot base (lane 0), for the issuing thread
   uint64_t* bar_d;               // hidden-layer D complete
@@ -288,7 +288,7 @@ struct RowChain2 {
 };
 
 template <int NWG>
-struct TcShared2 {
+struct TcShared {
   uint64_t bar_d[NWG];
   uint64_t bar_o[NWG];
   uint32_t tmem_base;
@@ -296,7 +296,7 @@ struct TcShared2 {
 };
 
 template <int NWG>
-__device__ __forceinline__ RowChain2 tc_setup2(TcShared2<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
+__device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
                                                int w_bytes) {
   const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
   for (int i = tid * 16; i < w_bytes; i += blockDim.x * 16)
@@ -314,7 +314,7 @@ __device__ __forceinline__ RowChain2 tc_setup2(TcShared2<NWG>& sh, uint8_t* s_we
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  RowChain2 c;
+  RowChain c;
   // warp-uniform values are broadcast with shfl so that the compiler can keep them in uniform registers
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0), wg_u = warp_u >> 2;
   c.d_slot = __shfl_sync(0xffffffffu, sh.tmem_base, 0) + wg_u * kSlotCols;
@@ -333,7 +333,7 @@ __device__ __forceinline__ RowChain2 tc_setup2(TcShared2<NWG>& sh, uint8_t* s_we
 }
 
 template <int NWG>
-__device__ __forceinline__ void tc_teardown2(TcShared2<NWG>& sh) {
+__device__ __forceinline__ void tc_teardown(TcShared<NWG>& sh) {
   tc_fence_before();
   __syncthreads();
   if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem_base, 512);
@@ -341,7 +341,7 @@ __device__ __forceinline__ void tc_teardown2(TcShared2<NWG>& sh) {
 
 // one K-step of layer (K-major B block at b0, N columns): D[d_col] (+)= A[a_col + 8 kk] * B
 template <int N>
-__device__ __forceinline__ void umma_step(const RowChain2& c, uint32_t b0, int d_col, int a_col, int kk) {
+__device__ __forceinline__ void umma_step(const RowChain& c, uint32_t b0, int d_col, int a_col, int kk) {
   constexpr uint32_t lbo = (uint32_t)(N / 8) * 128u;
   umma_ts_f16(c.d_slot + d_col, c.d_slot + a_col + kk * 8, smem_desc_kmajor(b0 + kk * 2 * lbo, lbo, 128),
               idesc_f16_m128(N), kk > 0 ? 1u : 0u);
@@ -349,7 +349,7 @@ __device__ __forceinline__ void umma_step(const RowChain2& c, uint32_t b0, int d
 
 // every thread's TMEM stores / loads of this step are done -> the warpgroup's issuer runs `f`
 template <class F>
-__device__ __forceinline__ void chain2_sync_issue(RowChain2& c, F&& f) {
+__device__ __forceinline__ void chain_sync_issue(RowChain& c, F&& f) {
   tmem_wait_st();
   tc_fence_before();
   wg_sync(c.bar_id);
@@ -362,28 +362,28 @@ __device__ __forceinline__ void chain2_sync_issue(RowChain2& c, F&& f) {
 // stage the input row of the next item (INW packed fp16x2 words, ones-padded); A_in is free as soon as
 // the L0 of the current item has completed, i.e. any time after the item's first epilogue
 template <int INW>
-__device__ __forceinline__ void chain2_stage(RowChain2& c, const uint32_t (&in)[INW]) {
+__device__ __forceinline__ void chain_stage(RowChain& c, const uint32_t (&in)[INW]) {
   static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
   if constexpr (INW == 8) tmem_st8(c.t_in, in); else tmem_st16(c.t_in, in);
 }
 
 // first item of a sequence: L0 alone
 template <int INW>
-__device__ __forceinline__ void chain2_begin(RowChain2& c) {
-  chain2_sync_issue(c, [&]() {
+__device__ __forceinline__ void chain_begin(RowChain& c) {
+  chain_sync_issue(c, [&]() {
 #pragma unroll
     for (int kk = 0; kk < INW / 8; ++kk) umma_step<64>(c, c.w_saddr, 0, kInCol, kk);
     umma_commit(c.bar_d);
   });
 }
 
-__device__ __forceinline__ void chain2_wait_d(RowChain2& c) {
+__device__ __forceinline__ void chain_wait_d(RowChain& c) {
   mbar_wait(c.bar_d, c.par_d);
   c.par_d ^= 1;
   tc_fence_after();
 }
 
-__device__ __forceinline__ void chain2_epilogue(RowChain2& c) {
+__device__ __forceinline__ void chain_epilogue(RowChain& c) {
   uint32_t v[32], w[32];
   tmem_ld32(c.t_d, v);
   tmem_ld32(c.t_d + 32, w);
@@ -399,17 +399,17 @@ __device__ __forceinline__ void chain2_epilogue(RowChain2& c) {
 
 // hidden part of the current item (its L0 is in flight): L0 -> L1 -> L2 -> h3 stored.  `shadow1()` runs
 // right after L1 has been issued, `shadow2()` right after L2: consume the previous item's output
-// (chain2_output) and issue the next item's loads in the first, stage the next item's input
-// (chain2_stage) in the second -- the loads then have a whole round trip to land.
+// (chain_output) and issue the next item's loads in the first, stage the next item's input
+// (chain_stage) in the second -- the loads then have a whole round trip to land.
 template <int INW, class Shadow1, class Shadow2>
-__device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, Shadow2&& shadow2) {
+__device__ __forceinline__ void chain_hidden(RowChain& c, Shadow1&& shadow1, Shadow2&& shadow2) {
   constexpr int off1 = 2 * INW * 64 * 2, off2 = off1 + 64 * 64 * 2;
   BNV_PROF_MARK(p0);
-  chain2_wait_d(c);
+  chain_wait_d(c);
   BNV_PROF_ADD(0, p0);
   BNV_PROF_MARK(p1);
-  chain2_epilogue(c);
-  chain2_sync_issue(c, [&]() {
+  chain_epilogue(c);
+  chain_sync_issue(c, [&]() {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off1, 0, kACol, kk);
     umma_commit(c.bar_d);
@@ -419,11 +419,11 @@ __device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, S
   shadow1();
   BNV_PROF_ADD(2, p2);
   BNV_PROF_MARK(p3);
-  chain2_wait_d(c);
+  chain_wait_d(c);
   BNV_PROF_ADD(3, p3);
   BNV_PROF_MARK(p4);
-  chain2_epilogue(c);
-  chain2_sync_issue(c, [&]() {
+  chain_epilogue(c);
+  chain_sync_issue(c, [&]() {
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off2, 0, kACol, kk);
     umma_commit(c.bar_d);
@@ -433,20 +433,20 @@ __device__ __forceinline__ void chain2_hidden(RowChain2& c, Shadow1&& shadow1, S
   shadow2();
   BNV_PROF_ADD(5, p5);
   BNV_PROF_MARK(p6);
-  chain2_wait_d(c);
+  chain_wait_d(c);
   BNV_PROF_ADD(6, p6);
   BNV_PROF_MARK(p7);
-  chain2_epilogue(c);
+  chain_epilogue(c);
   BNV_PROF_ADD(7, p7);
 }
 
 // output layer of the current item + (has_next) L0 of the staged next item, interleaved in one burst:
 // the two accumulate into different TMEM columns, so their K-steps do not serialise on each other
 template <int INW>
-__device__ __forceinline__ void chain2_finish(RowChain2& c, bool has_next) {
+__device__ __forceinline__ void chain_finish(RowChain& c, bool has_next) {
   constexpr int off3 = 2 * INW * 64 * 2 + 2 * 64 * 64 * 2;
   BNV_PROF_MARK(p8);
-  chain2_sync_issue(c, [&]() {
+  chain_sync_issue(c, [&]() {
     if (has_next) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
@@ -465,9 +465,9 @@ __device__ __forceinline__ void chain2_finish(RowChain2& c, bool has_next) {
   BNV_PROF_COUNT(11);
 }
 
-// read the NOUT outputs of the item whose chain2_finish was issued last (waits for its output layer)
+// read the NOUT outputs of the item whose chain_finish was issued last (waits for its output layer)
 template <int NOUT>
-__device__ __forceinline__ void chain2_output(RowChain2& c, float (&out)[NOUT]) {
+__device__ __forceinline__ void chain_output(RowChain& c, float (&out)[NOUT]) {
   static_assert(NOUT == 8 || NOUT == 1, "n_out must be 8 or 1");
   mbar_wait(c.bar_o, c.par_o);
   c.par_o ^= 1;

@@ -1,12 +1,13 @@
-// tcgen05 kernels on the software-pipelined chain (engine v2, bnv_tc.cuh): plain MLP forward, fused
-// encode (backproject -> 8 corner rows -> encoder MLP -> scatter), fused decode (8-corner gather ->
-// decoder MLP -> trilinear blend + prior) and the G table of the factored meshlize decode.
+// tcgen05 kernels on the software-pipelined chain (bnv_tc.cuh): plain MLP forward, fused encode
+// (backproject -> 8 corner rows -> encoder MLP -> scatter), fused decode (8-corner gather -> decoder MLP ->
+// trilinear blend + prior) and the G table of the factored meshlize decode.
 //
-// Differences to the first-generation kernels (bnv_tc.cu):
-//  * the output layer runs on the tensor core and is issued together with the next item's first layer;
-//    its result is consumed in the shadow of the next item -> 3 exposed MMA round trips per item;
-//  * the encode kernel splits the frame at (tile, corner) granularity: every chain gets the same number
-//    of corner rows (+-1), which removes the 4-vs-5-tiles tail of the per-tile split;
+//  * every item (one 128-row tile through the MLP) costs three exposed MMA round trips: the output layer runs on
+//    the tensor core and is issued together with the next item's first layer, its result is consumed in the
+//    shadow of the next item;
+//  * the encode kernel splits the frame at (tile, corner) granularity: every chain gets the same number of
+//    corner rows (+-1); the claim CAS of a tile are issued in its prologue and settled in the shadow of its
+//    first round;
 //  * in the tile shard, the corners nobody in the warpgroup owns are dropped from the item list up front.
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -28,7 +29,7 @@ constexpr int kThreads = kNWG * 128;
 constexpr uint32_t kOnes = 0x3C003C00u;       // fp16x2 {1.0, 1.0}: tcnn pads the input with ones
 
 struct alignas(16) Smem {
-  TcShared2<kNWG> sh;
+  TcShared<kNWG> sh;
   int32_t slot[8][kThreads];   // encode: scratch row of (this thread's point, corner k); thread-private, [k][tid]
 };
 
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
                                                                       float* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t n_tiles = (n + 127) / 128;
   const int64_t stride = (int64_t)gridDim.x * kNWG;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
   auto drain = [&]() {
     if (pend >= 0) {
       float out[NOUT];
-      chain2_output<NOUT>(c, out);
+      chain_output<NOUT>(c, out);
       if (pend < n) {
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) y[pend * NOUT + o] = out[o];
@@ -86,25 +87,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
   if (tile < n_tiles) {
     uint32_t in[INW];
     load_row<NIN, INW>(x, tile * 128 + r, n, in);
-    chain2_stage<INW>(c, in);
-    chain2_begin<INW>(c);
+    chain_stage<INW>(c, in);
+    chain_begin<INW>(c);
     for (; tile < n_tiles; tile += stride) {
       const bool has_next = tile + stride < n_tiles;
-      chain2_hidden<INW>(
+      chain_hidden<INW>(
           c,
           [&]() {
             drain();
             if (has_next) load_row<NIN, INW>(x, (tile + stride) * 128 + r, n, in);
           },
           [&]() {
-            if (has_next) chain2_stage<INW>(c, in);
+            if (has_next) chain_stage<INW>(c, in);
           });
-      chain2_finish<INW>(c, has_next);
+      chain_finish<INW>(c, has_next);
       pend = tile * 128 + r;
     }
     drain();
   }
-  tc_teardown2<kNWG>(S.sh);
+  tc_teardown<kNWG>(S.sh);
 }
 
 // ---- fused encode -----------------------------------------------------------------------------------
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
   // 4 no claims (+ no reductions), 8 whole tiles per chain instead of the (tile, corner) split
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5;
   const GeomDev& g = m.g;
   // (u - cx) / fx and (v - cy) / fy in float64 for every column / row, once per CTA (bnv_frame.cuh)
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     if (pending) {
       float y[8];
       if (debug & 1) { for (int j = 0; j < 8; ++j) y[j] = (float)j; } else
-      chain2_output<8>(c, y);
+      chain_output<8>(c, y);
       if (debug & 16) { if (!(debug & 6)) add_row_f32_runs(m, pend_slot, y); } else
       if (pend_slot >= 0 && !(debug & 6)) add_row_f32(m, pend_slot, y);
       pending = false;
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     {
       uint32_t in[8];
       enc_input(__ffs(live) - 1, cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
-      chain2_stage<8>(c, in);
-      chain2_begin<8>(c);
+      chain_stage<8>(c, in);
+      chain_begin<8>(c);
     }
     bool first = true;
 #pragma unroll 1
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       const int k = __ffs(rem) - 1;
       rem &= rem - 1;
       const bool has_next = rem != 0;
-      chain2_hidden<8>(
+      chain_hidden<8>(
           c,
           [&]() {
             drain();
@@ -292,11 +293,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
             if (has_next) {
               uint32_t in[8];
               enc_input(__ffs(rem) - 1, cc, fl, ce, g.vs, g.inv_vs, nrm01, nrm2o, in);
-              chain2_stage<8>(c, in);
+              chain_stage<8>(c, in);
             }
           });
       first = false;
-      chain2_finish<8>(c, has_next);
+      chain_finish<8>(c, has_next);
       pending = true;
       pend_slot = S.slot[k][threadIdx.x];
     }
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
     atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)st_rows);
     atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)st_inb);
   }
-  tc_teardown2<kNWG>(S.sh);
+  tc_teardown<kNWG>(S.sh);
 }
 
 // ---- fused decode -----------------------------------------------------------------------------------
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
                                                                  const uint8_t* __restrict__ gW, int w_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   DecState& Q = *reinterpret_cast<DecState*>(weights_smem(smem) + ((w_bytes + 127) / 128) * 128);
   const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     const uint32_t in[16] = {f.x, f.y, f.z, f.w,
                              Q.w_ls[0][sx][tid], Q.w_c1[0][sx][tid], Q.w_ls[1][sy][tid], Q.w_c1[1][sy][tid],
                              Q.w_ls[2][sz][tid], Q.w_c1[2][sz][tid], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
-    chain2_stage<16>(c, in);
+    chain_stage<16>(c, in);
   };
   // the query whose last corner is still in D_out
   bool pending = false, p_live = false;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
   auto drain = [&]() {
     if (pending) {
       float y[1];
-      chain2_output<1>(c, y);
+      chain_output<1>(c, y);
       p_sdf = __fadd_rn(p_sdf, __fmul_rn(__fmul_rn(y[0], g.vs), p_wn));                   // D4, D5 (corner 7)
       if (has_prior) p_dsum = __fadd_rn(p_dsum, __fmul_rn(p_dl, p_wn));                  // D6
       if (p_live) {
@@ -446,20 +447,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     drain();
     float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
     stage_corner(0, f_nxt);
-    chain2_begin<16>(c);
+    chain_begin<16>(c);
     BNV_PROF_ADD(9, p_pre);
     float w_cur = w_nxt;
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
       minw = fminf(minw, w_cur);                                                         // D3
-      chain2_hidden<16>(
+      chain_hidden<16>(
           c,
           [&]() {
             // shadow of the second layer: issue the next corner's gather, blend the previous corner
             if (k < 7) gather(k + 1, f_nxt, w_nxt);
             if (k > 0) {
               float y[1];
-              chain2_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
+              chain_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
               const float wn = __fdiv_rn(weight_of(k - 1), wsum);                        // D2
               sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                // D4, D5
               if (has_prior) dsum = __fadd_rn(dsum, __fmul_rn(prior_of(k - 1), wn));     // D6
@@ -469,7 +470,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
             // shadow of the third layer: the gather has landed -> stage the next corner's row
             if (k < 7) stage_corner(k + 1, f_nxt);
           });
-      chain2_finish<16>(c, k < 7);
+      chain_finish<16>(c, k < 7);
       w_cur = w_nxt;
     }
     // corner 7 is in flight: finish this query at the top of the next tile (or after the loop)
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
   }
   drain();
   BNV_PROF_ADD(10, p_life);
-  tc_teardown2<kNWG>(S.sh);
+  tc_teardown<kNWG>(S.sh);
 }
 
 // ---- factored decode of the meshlize sample blocks: G[V][l] table (see bnv_tc.cu) ----------------------
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __r
                                                                  float* __restrict__ G) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain2 c = tc_setup2<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t total = (n_rows + 1) * 27;                       // voxel n_rows = the miss voxel
   const int64_t n_tiles = (total + 127) / 128;
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __r
   auto drain = [&]() {
     if (pend >= 0) {
       float y[1];
-      chain2_output<1>(c, y);
+      chain_output<1>(c, y);
       if (pend < total) G[pend] = y[0];
     }
     pend = -1;
@@ -535,25 +536,25 @@ __global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __r
   if (tile < n_tiles) {
     uint32_t in[16];
     make_row(tile * 128 + r, in);
-    chain2_stage<16>(c, in);
-    chain2_begin<16>(c);
+    chain_stage<16>(c, in);
+    chain_begin<16>(c);
     for (; tile < n_tiles; tile += stride) {
       const bool has_next = tile + stride < n_tiles;
-      chain2_hidden<16>(
+      chain_hidden<16>(
           c,
           [&]() {
             drain();
             if (has_next) make_row((tile + stride) * 128 + r, in);
           },
           [&]() {
-            if (has_next) chain2_stage<16>(c, in);
+            if (has_next) chain_stage<16>(c, in);
           });
-      chain2_finish<16>(c, has_next);
+      chain_finish<16>(c, has_next);
       pend = tile * 128 + r;
     }
     drain();
   }
-  tc_teardown2<kNWG>(S.sh);
+  tc_teardown<kNWG>(S.sh);
 }
 
 }  // namespace tcc

@@ -8,26 +8,26 @@ using namespace bnv::tc;
 
 __device__ __forceinline__ long long clk() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 
-struct alignas(16) Smem { TcShared2<4> sh; };
+struct alignas(16) Smem { TcShared<4> sh; };
 
 template <int NWG>
 __global__ void __launch_bounds__(NWG * 128, 1) k_chain(const uint8_t* gW, int w_bytes, int rounds, long long* out) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
   uint8_t* s_w = smem + 256;
-  RowChain2 c = tc_setup2<4>(S.sh, s_w, gW, w_bytes);
+  RowChain c = tc_setup<4>(S.sh, s_w, gW, w_bytes);
   const int wg = threadIdx.x >> 7;
   const bool rec = (threadIdx.x & 127) == 0;
   uint32_t in[16];
   for (int i = 0; i < 16; ++i) in[i] = 0x3C003C00u;
   long long a_ld = 0, a_cvt = 0, a_st = 0, a_sync = 0, a_issue = 0, a_wait = 0;
   constexpr int off1 = 32 * 64 * 2;
-  chain2_stage<16>(c, in);
-  chain2_begin<16>(c);
+  chain_stage<16>(c, in);
+  chain_begin<16>(c);
   long long t_issue = clk();
   const long long t_start = t_issue;
   for (int r = 0; r < rounds; ++r) {
-    chain2_wait_d(c);
+    chain_wait_d(c);
     const long long t0 = clk();
     uint32_t v[32], w[32];
     tmem_ld32(c.t_d, v);
@@ -59,13 +59,13 @@ __global__ void __launch_bounds__(NWG * 128, 1) k_chain(const uint8_t* gW, int w
     a_wait += t0 - t_issue; a_ld += t1 - t0; a_cvt += t2 - t1; a_st += t3 - t2; a_sync += t4 - t3; a_issue += t5 - t4;
     t_issue = t5;
   }
-  chain2_wait_d(c);
+  chain_wait_d(c);
   const long long t_end = clk();
   if (rec && wg < NWG) {
     long long* o = out + (blockIdx.x * 4 + wg) * 8;
     o[0] = a_wait; o[1] = a_ld; o[2] = a_cvt; o[3] = a_st; o[4] = a_sync; o[5] = a_issue; o[6] = t_end - t_start;
   }
-  tc_teardown2<4>(S.sh);
+  tc_teardown<4>(S.sh);
 }
 
 template <int NWG> void run(const uint8_t* dW, int wbytes, long long* d, long long* h) {
