@@ -415,7 +415,8 @@ def run_b200(args):
                        "active_voxels_rank0": A, "ms": dec_ms_job,
                        "path": "bnv_decode_voxel_blocks (meshlize samples): G[voxel][offset] table on the tensor cores + blend",
                        "roofline": {"bound": "tensor", "achieved": exe_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                                    "frac": exe_tflops / pk["tf_sustained"], "algorithmic_tflops": dec_tflops,
+                                    "frac": exe_tflops / pk["tf_sustained"], "frac_of_burst_peak": exe_tflops / pk["tf_burst"],
+                                    "algorithmic_tflops": dec_tflops,
                                     "traffic": ((traffic("gtable_tc_kernel") or 0) + (traffic("blend_blocks_kernel") or 0)) or None
                                                if config.mlp_mode_name() == "tc16" else traffic("decode_simt_kernel"),
                                     "peak_source": pk["src"],
@@ -428,6 +429,7 @@ def run_b200(args):
                                    "what": "same queries through bnv_decode_sdf (arbitrary coordinates, 8 MLP rows per query)",
                                    "roofline": {"bound": "tensor", "achieved": gen_tflops, "peak": pk["tf_sustained"],
                                                 "unit": "TFLOP/s", "frac": gen_tflops / pk["tf_sustained"],
+                                                "frac_of_burst_peak": gen_tflops / pk["tf_burst"],
                                                 "traffic": traffic("decode_tc_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel")}}},
             "cpu_baseline": cpu,
         }
