@@ -40,6 +40,11 @@ def test_bad_arguments_fail_loudly_without_gpu():
     assert rc == -1 and b"null" in lib.bnv_last_error()
     rc = lib.bnv_mlp_create(ctypes.byref(h), None, 0, 6, 8, 0)
     assert rc == -1
+    # host-buffer call and the experimental exchange validate their arguments before touching CUDA
+    assert lib.bnv_fuse_frame_host(None, None, 480, 640, None, None, 3.0, None, 8, 1, None, None, None) == -1
+    assert lib.bnv_exchange_create(ctypes.byref(h), None, 1024) == -1
+    assert lib.bnv_exchange_push(None, None) == -1 and lib.bnv_exchange_join(None, None) == -1
+    assert lib.bnv_exchange_destroy(None) == 0
 
 
 def test_sass_is_sm100a():
