@@ -438,6 +438,91 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------- #
+def run_paced(args):
+    """BASELINE.json configs[4]: ARKit-shape 256x192 depth at a paced frame rate (default 60 fps), 2 cm voxels,
+    10 % invalidated pixels; per-frame latency = host frame available -> frame statistics read back on the host
+    (bnv_fuse_frame_host + stream sync; tile shard with its boundary exchange when launched on N > 1 GPUs).
+    Opt-in (`--paced-fps 60`); prints its own JSON line (sustained fps, latency p50 / p99 / max, late frames)."""
+    import torch
+    import torch.distributed as dist
+    from bnv_fusion_b200 import config, synth
+    from bnv_fusion_b200.model import LitFusionPointNet
+    from bnv_fusion_b200.volume import SparseVolume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if args.mlp:
+        config.set_mlp_mode(args.mlp)
+    spec = synth.stream_spec("arkit")
+    n_src = 32
+    frames = [synth.make_frame(spec, i, seed=0) for i in range(n_src)]
+    p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
+    cfg = {"trainer": {"dense_volume": False},
+           "model": {"feature_vector_size": 8, "voxel_size": spec.voxel_size, "min_pts_in_grid": 8,
+                     "point_net": {"in_channels": 6}, "nerf": {"num_encoding_fn_xyz": 1}}}
+    model = LitFusionPointNet(cfg)
+    model.load_state_dict({"pointnet_backbone.model.params": torch.from_numpy(p["encoder"]),
+                           "nerf.model.params": torch.from_numpy(p["decoder"])})
+    model.eval(); model.cuda(); model.freeze()
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    target, pre = model, (vol,)
+    if world > 1:
+        from bnv_fusion_b200.dist import TileShardedFusion
+        target, pre = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange), ()
+    host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
+    stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+    def one(i):
+        _, K, T = frames[i % n_src]
+        target.fuse_depth_frame_host(*pre, host[i % n_src], K, T, spec.max_depth, stats_host=stats_host,
+                                     next_depth_mm_host=host[(i + 1) % n_src])
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(max(args.warmup, 10)):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = max(args.steps, 300)
+    period = 1.0 / args.paced_fps
+    lat = np.zeros(n)
+    t0 = time.perf_counter() + 0.01
+    for i in range(n):
+        t_avail = t0 + i * period                   # the sensor delivers frame i at this instant
+        while time.perf_counter() < t_avail:
+            pass
+        one(i)
+        lat[i] = time.perf_counter() - t_avail
+    total = time.perf_counter() - t0
+    vol.check_status()
+    p50, p99, mx = (float(np.percentile(lat, q)) * 1e3 for q in (50, 99, 100))
+    late = int((lat > period).sum())
+    if world > 1:
+        t = torch.tensor([p50, p99, mx, float(late), total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        p50, p99, mx, late, total = float(t[0]), float(t[1]), float(t[2]), int(t[3]), float(t[4])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "paced_stream_frame_latency_ms", "value": p99, "unit": "ms (p99, max over ranks)", "n_gpus": world,
+            "steps": n, "warmup": max(args.warmup, 10), "higher_is_better": False, "data": "synthetic",
+            "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
+            "config": {"workload": "arkit 256x192 depth, 2 cm voxels, 10 % invalidated pixels, paced live stream",
+                       "paced_fps": args.paced_fps,
+                       "parallelism": "1 GPU" if world == 1 else f"tile shard over {world} GPUs ({args.exchange} exchange)"},
+            "latency_ms": {"p50": p50, "p99": p99, "max": mx}, "late_frames": late,
+            "sustained_fps": n / total, "frame_budget_ms": period * 1e3,
+            "what": "host frame available -> H2D -> fuse (+ boundary exchange enqueued) -> frame statistics on the host"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,6 +531,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--paced-fps", type=float, default=0.0,
+                    help="opt-in: BASELINE configs[4] paced ARKit-shape stream (e.g. 60), prints latency percentiles instead")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="tile shard boundary exchange: one NCCL all-gather per frame (default) or the experimental "
                          "peer-memory routing (csrc/bnv_p2p.cu)")
@@ -457,6 +544,8 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["BNV_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
+    elif args.paced_fps > 0:
+        run_paced(args)
     else:
         run_b200(args)
 
