@@ -56,6 +56,7 @@ SIGNATURES = {
     "bnv_exchange_create": (C.c_int, [C.POINTER(_P), _P, _I64]),
     "bnv_exchange_handle": (C.c_int, [_P, _P]),
     "bnv_exchange_connect": (C.c_int, [_P, _P]),
+    "bnv_exchange_begin_frame": (C.c_int, [_P, _P]),
     "bnv_exchange_push": (C.c_int, [_P, _P]),
     "bnv_exchange_join": (C.c_int, [_P, _P]),
     "bnv_exchange_destroy": (C.c_int, [_P]),

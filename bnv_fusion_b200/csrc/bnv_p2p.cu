@@ -9,8 +9,9 @@
 // timeout, it holds no SM that the fusion kernels need) and upserts its inbox.  No collective kernel, no
 // all-to-all traffic, and the whole sharded step is reachable from one C call.
 //
-// Buffers are double-buffered by frame parity; a sender reuses parity b for frame s only after every peer
-// acknowledged frame s - 2 (ack sequence numbers written back the same way).
+// Everything but one event record / wait runs on the exchange's side stream, overlapped with the next frame.  The
+// local record buffers and the peers' inboxes are double-buffered by frame parity; a sender reuses parity b for
+// frame s only after every peer acknowledged frame s - 2 (ack sequence numbers written back the same way).
 //
 // Status: compiles for sm_100a; written at the end of round 1 without GPU time left, NOT yet run on
 // hardware -- the NCCL path stays the tested default.
@@ -175,16 +176,20 @@ struct bnv_exchange {
   int32_t* scratch;            // [kMaxPeers] sent counters | push done | insert done
   PeerPtrs peers;
   bool connected;
-  uint32_t seq;                // frames pushed so far
+  uint32_t seq;                // frames begun so far
+  int32_t* halo[2];            // this rank's boundary records, double-buffered by frame parity (attached to the map)
+  int64_t halo_cap;
   cudaStream_t side;
-  cudaEvent_t pushed, upserted;
+  cudaEvent_t fused, pushed[2], upserted;
+  bool pushed_valid[2];
   bool any_upsert;
+  bool frame_open;
 };
 
 extern "C" {
 
 int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_records) {
-  if (!out || !map || capacity_records <= 0) { set_error("bnv_exchange_create: bad argument"); return BNV_E_ARG; }
+  if (!out || !map || capacity_records <= 0 || capacity_records > 0x7fffffff) { set_error("bnv_exchange_create: bad argument"); return BNV_E_ARG; }
   const int world = map->d.g.world, rank = map->d.g.rank;
   if (world < 2 || world > kMaxPeers) { set_error("bnv_exchange_create: world must be 2..%d (call bnv_map_set_shard first)", kMaxPeers); return BNV_E_ARG; }
   bnv_exchange* ex = new (std::nothrow) bnv_exchange();
@@ -197,8 +202,14 @@ int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_r
   if (e == cudaSuccess) e = cudaMemset(ex->block, 0, bytes);
   if (e == cudaSuccess) e = cudaMalloc((void**)&ex->scratch, (kMaxPeers + 2) * 4);
   if (e == cudaSuccess) e = cudaMemset(ex->scratch, 0, (kMaxPeers + 2) * 4);
+  ex->halo_cap = capacity_records;
+  for (int i = 0; i < 2; ++i) {
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ex->halo[i], (10 + (size_t)capacity_records * kRecWords) * 4);
+    if (e == cudaSuccess) e = cudaMemset(ex->halo[i], 0, 40);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->pushed[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ex->side, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->pushed, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->fused, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->upserted, cudaEventDisableTiming);
   if (e != cudaSuccess) { set_error("bnv_exchange_create: %s", cudaGetErrorString(e)); return BNV_E_ALLOC; }
   BNV_CUDA(cudaDeviceSynchronize());
@@ -232,31 +243,52 @@ int bnv_exchange_connect(bnv_exchange_t* ex, const void* handles /* [world][64],
   return BNV_OK;
 }
 
-/* After bnv_fuse_frame* on `stream`: route this frame's boundary records to the peers (on `stream`), then wait
- * for every peer's records of the same frame and upsert them (on the exchange's side stream). */
-int bnv_exchange_push(bnv_exchange_t* ex, void* stream) {
-  if (!ex || !ex->connected) { set_error("bnv_exchange_push: exchange is not connected"); return BNV_E_ARG; }
-  if (!ex->map->d.halo) { set_error("bnv_exchange_push: no halo buffer attached to the map"); return BNV_E_ARG; }
+/* Start a frame on `stream`: attach the boundary-record buffer of this frame's parity to the map (once the push
+ * that last read it has finished) and reset its count.  Replaces bnv_map_set_halo_buffer + bnv_map_halo_begin. */
+int bnv_exchange_begin_frame(bnv_exchange_t* ex, void* stream) {
+  if (!ex || !ex->connected) { set_error("bnv_exchange_begin_frame: exchange is not connected"); return BNV_E_ARG; }
+  if (ex->frame_open) { set_error("bnv_exchange_begin_frame: the previous frame was not pushed"); return BNV_E_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
   const uint32_t seq = ++ex->seq;
+  const int buf = (int)(seq & 1u);
+  if (ex->pushed_valid[buf]) BNV_CUDA(cudaStreamWaitEvent(s, ex->pushed[buf], 0));     // frame seq - 2 has been routed
+  ex->map->d.halo = ex->halo[buf];
+  ex->map->d.halo_cap = (int32_t)ex->halo_cap;
+  BNV_CUDA(cudaMemsetAsync(ex->halo[buf], 0, 40, s));
+  ex->frame_open = true;
+  return BNV_OK;
+}
+
+/* After bnv_fuse_frame* on `stream`: everything else happens on the exchange's side stream, overlapped with the
+ * next frame -- route this frame's boundary records to the peers that need them, wait for every peer's records of
+ * the same frame, upsert them, acknowledge. */
+int bnv_exchange_push(bnv_exchange_t* ex, void* stream) {
+  if (!ex || !ex->connected) { set_error("bnv_exchange_push: exchange is not connected"); return BNV_E_ARG; }
+  if (!ex->frame_open) { set_error("bnv_exchange_push: call bnv_exchange_begin_frame first"); return BNV_E_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const uint32_t seq = ex->seq;
   const int buf = (int)(seq & 1u);
   const long long timeout = 4000000000ll;                       // ~2 s of SM clock
   uint32_t* flags_ready = reinterpret_cast<uint32_t*>(ex->block);
   uint32_t* flags_ack = flags_ready + kMaxPeers;
-  if (seq > 2) {                                                // parity `buf` was last used by frame seq - 2
-    wait_flags_kernel<<<1, 32, 0, s>>>(flags_ack, seq - 2, ex->world, ex->rank, timeout, &ex->map->d.ctr[2]);
+  BNV_CUDA(cudaEventRecord(ex->fused, s));
+  BNV_CUDA(cudaStreamWaitEvent(ex->side, ex->fused, 0));
+  if (seq > 2) {                                                // the peers' inbox parity `buf` was last used by frame seq - 2
+    wait_flags_kernel<<<1, 32, 0, ex->side>>>(flags_ack, seq - 2, ex->world, ex->rank, timeout, &ex->map->d.ctr[2]);
     BNV_LAUNCH_CHECK("wait_flags_kernel");
   }
-  halo_push_kernel<<<64, 256, 0, s>>>(ex->map->d, ex->peers, buf, seq, ex->cap, ex->scratch, ex->scratch + kMaxPeers);
+  MapDev d = ex->map->d;                                         // carries this frame's halo pointer
+  halo_push_kernel<<<64, 256, 0, ex->side>>>(d, ex->peers, buf, seq, ex->cap, ex->scratch, ex->scratch + kMaxPeers);
   BNV_LAUNCH_CHECK("halo_push_kernel");
-  BNV_CUDA(cudaEventRecord(ex->pushed, s));
-  BNV_CUDA(cudaStreamWaitEvent(ex->side, ex->pushed, 0));
+  BNV_CUDA(cudaEventRecord(ex->pushed[buf], ex->side));
+  ex->pushed_valid[buf] = true;
   wait_flags_kernel<<<1, 32, 0, ex->side>>>(flags_ready, seq, ex->world, ex->rank, timeout, &ex->map->d.ctr[2]);
   BNV_LAUNCH_CHECK("wait_flags_kernel");
-  insert_inbox_kernel<<<64, 256, 0, ex->side>>>(ex->map->d, ex->peers, buf, seq, ex->cap, ex->scratch + kMaxPeers + 1);
+  insert_inbox_kernel<<<64, 256, 0, ex->side>>>(d, ex->peers, buf, seq, ex->cap, ex->scratch + kMaxPeers + 1);
   BNV_LAUNCH_CHECK("insert_inbox_kernel");
   BNV_CUDA(cudaEventRecord(ex->upserted, ex->side));
   ex->any_upsert = true;
+  ex->frame_open = false;
   return BNV_OK;
 }
 
@@ -275,8 +307,14 @@ int bnv_exchange_destroy(bnv_exchange_t* ex) {
     if (r != ex->rank && ex->peers.base[r]) cudaIpcCloseMemHandle(ex->peers.base[r]);
   if (ex->block) cudaFree(ex->block);
   if (ex->scratch) cudaFree(ex->scratch);
+  ex->map->d.halo = nullptr;
+  ex->map->d.halo_cap = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (ex->halo[i]) cudaFree(ex->halo[i]);
+    if (ex->pushed[i]) cudaEventDestroy(ex->pushed[i]);
+  }
   if (ex->side) cudaStreamDestroy(ex->side);
-  if (ex->pushed) cudaEventDestroy(ex->pushed);
+  if (ex->fused) cudaEventDestroy(ex->fused);
   if (ex->upserted) cudaEventDestroy(ex->upserted);
   delete ex;
   return BNV_OK;

@@ -157,8 +157,8 @@ class TileShardedFusion:
         import torch.distributed as dist
         torch = self.torch
         v, lib = self.volume, self._lib
-        if self._ex is not None:                 # peer-memory exchange: routing + waits live in the library
-            lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
+        if self._ex is not None:                 # peer-memory exchange: buffers, routing and waits live in the library
+            lib.check(v._lib.bnv_exchange_begin_frame(self._ex, v._stream()), "bnv_exchange_begin_frame")
             fuse_call()
             lib.check(v._lib.bnv_exchange_push(self._ex, v._stream()), "bnv_exchange_push")
             return

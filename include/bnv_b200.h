@@ -110,13 +110,15 @@ int bnv_map_insert_halo(bnv_map_t* map, const void* gathered_dev, int world, int
  * all-gather path above is the default): the sender routes each boundary record straight into the inbox of
  * the ranks that need it (stores over NVLink into cudaIpc-mapped memory), the receiver upserts its inbox on a
  * side stream once every peer's frame sequence number has arrived.  Usage, one process per GPU:
- *   bnv_map_set_shard + bnv_map_set_halo_buffer, bnv_exchange_create, bnv_exchange_handle (64 bytes),
- *   all-gather the handles by any transport, bnv_exchange_connect; then per frame, on every rank:
- *   bnv_map_halo_begin, bnv_fuse_frame*, bnv_exchange_push; bnv_exchange_join before reading the map. */
+ *   bnv_map_set_shard, bnv_exchange_create, bnv_exchange_handle (64 bytes), all-gather the handles by any
+ *   transport, bnv_exchange_connect; then per frame, on every rank: bnv_exchange_begin_frame (attaches and
+ *   resets this frame's record buffer), bnv_fuse_frame*, bnv_exchange_push; bnv_exchange_join before reading
+ *   the map.  Only an event record / wait touches the fusing stream; routing and upsert run on a side stream. */
 typedef struct bnv_exchange bnv_exchange_t;
 int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_records_per_peer);
 int bnv_exchange_handle(bnv_exchange_t* ex, void* handle64_out_host);
 int bnv_exchange_connect(bnv_exchange_t* ex, const void* handles_host /* [world][64], rank order */);
+int bnv_exchange_begin_frame(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_push(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_join(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_destroy(bnv_exchange_t* ex);
