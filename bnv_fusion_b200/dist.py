@@ -90,6 +90,22 @@ def select_needed(flat, n_xyz, rank, world, brick_log2):
     return need
 
 
+def needed_by(flat, n_xyz, world, brick_log2):
+    """sender-side routing rule of the peer-memory exchange (csrc/bnv_p2p.cu halo_push_kernel): bit p of the
+    result is set iff rank p owns a brick in the voxel's 26-neighbourhood, i.e. iff `select_needed(..., rank=p)`"""
+    ijk = unflatten(flat, n_xyz)
+    n = np.asarray(n_xyz, np.int64)
+    mask = np.zeros(len(ijk), np.int64)
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                q = ijk + np.array([dx, dy, dz])
+                inside = ((q >= 0) & (q < n)).all(axis=-1)
+                own = owner_of(np.clip(q, 0, n - 1), world, brick_log2)
+                mask |= np.where(inside, np.int64(1) << own, 0)
+    return mask
+
+
 class TileShardedFusion:
     """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
 

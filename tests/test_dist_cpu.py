@@ -1,4 +1,4 @@
-"""CPU, gloo, world_size 2: the tile-shard logic (ownership, one all-gather per frame of boundary
+"""CPU, gloo, world_size 2 and 3: the tile-shard logic (ownership, one all-gather per frame of boundary
 records, halo selection) on top of the numpy oracle.  The union of the ranks' owned voxels must equal
 the single-process map bit for bit, and every rank must hold the halo voxels its own queries need."""
 import os
@@ -77,8 +77,8 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_tile_shard_world2(tmp_path, tcnn_params):
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_shard_gloo(tmp_path, tcnn_params, world):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     # single-process reference
@@ -140,3 +140,16 @@ def test_halo_buffer_protocol():
     # (5,5,5) sits inside brick (1,1,1) (rank 1): only rank 1 touches it; (4,0,0) touches brick (0,0,0) of rank 0
     assert D.select_needed(flat, (32, 32, 32), 0, 2, 2).tolist() == [True, True, True, False, True]
     assert D.select_needed(flat, (32, 32, 32), 1, 2, 2).tolist() == [False, True, True, True, True]
+
+
+def test_sender_side_routing_equals_receiver_side_selection():
+    """the peer-memory exchange routes at the sender (`needed_by`, mirrored by halo_push_kernel); the all-gather
+    path filters at the receiver (`select_needed`, mirrored by insert_halo_kernel): same rule, both directions"""
+    rng = np.random.default_rng(1)
+    n_xyz = (40, 33, 37)
+    flat = rng.integers(0, n_xyz[0] * n_xyz[1] * n_xyz[2], 3000)
+    flat = np.concatenate([flat, [0, n_xyz[0] * n_xyz[1] * n_xyz[2] - 1]])          # grid corners: clipped neighbourhoods
+    for world, b in ((2, 2), (3, 1), (8, 2), (5, 3)):
+        mask = D.needed_by(flat, n_xyz, world, b)
+        for rank in range(world):
+            assert np.array_equal((mask >> rank) & 1, D.select_needed(flat, n_xyz, rank, world, b).astype(np.int64))
