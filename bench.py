@@ -152,6 +152,64 @@ def run_reference(args):
     }))
 
 
+
+def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick_log2, exchange, n_frames=8):
+    """N > 1 only: every rank fuses the first `n_frames` frames into a fresh tile-sharded map; rank 0 fuses the same
+    frames into an UNSHARDED map and compares it with the union of the ranks' owned voxels: keys and fusion weights
+    bit-exact, features <= 5e-5 (fp32 summation order), the 27 meshlize samples of every owned voxel (decoded on
+    its owner from halo copies of foreign corners) <= 1e-4.  Returns the dict printed as "shard_parity"."""
+    from bnv_fusion_b200.volume import SparseVolume
+    from bnv_fusion_b200.dist import TileShardedFusion
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
+    sh = TileShardedFusion(vol, model, rank, world, brick_log2=brick_log2, exchange=exchange)
+    devf = [torch.from_numpy(frames[i][0].view(np.int16).copy()).to(dev).view(torch.uint16) for i in range(n_frames)]
+    for i in range(n_frames):
+        sh.fuse_depth_frame(devf[i], frames[i][1], frames[i][2], spec.max_depth)
+    vol.check_status()
+    vol.to_tensor()
+    vol.weights += 8.0
+    sdf = vol.decode_voxel_blocks(model.nerf).reshape(-1, 27)
+    own = sh.owned_rows()
+    n = vol._n_xyz_host
+    c = vol.active_coordinates[own]
+    rec = torch.cat([(c[:, 0] * (n[1] * n[2]) + c[:, 1] * n[2] + c[:, 2]).double()[:, None],
+                     vol.weights[own].double(), vol.features[own].double(), sdf[own].double()], dim=1).contiguous()
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = rec.shape[0]
+    dist.all_reduce(sizes)
+    cap = int(sizes.max())
+    pad = torch.zeros((cap, rec.shape[1]), dtype=torch.float64, device=dev)
+    pad[: rec.shape[0]] = rec
+    allr = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, allr, dst=0)
+    sh.detach()
+    out = None
+    if rank == 0:
+        got = torch.cat([allr[r][: int(sizes[r])] for r in range(world)], dim=0)
+        got = got[torch.argsort(got[:, 0])]
+        ref = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
+        for i in range(n_frames):
+            model.fuse_depth_frame(ref, devf[i], frames[i][1], frames[i][2], spec.max_depth)
+        ref.check_status()
+        ref.to_tensor()
+        ref.weights += 8.0
+        rsdf = ref.decode_voxel_blocks(model.nerf).reshape(-1, 27)
+        rc = ref.active_coordinates
+        rflat = rc[:, 0] * (n[1] * n[2]) + rc[:, 1] * n[2] + rc[:, 2]
+        order = torch.argsort(rflat)
+        keys_equal = got.shape[0] == rflat.shape[0] and bool((got[:, 0].long() == rflat[order]).all())
+        out = {"frames": n_frames, "voxels": int(rflat.shape[0]), "owned_per_rank": [int(v) for v in sizes.tolist()],
+               "keys_equal": keys_equal, "weights_equal": False, "max_dfeat": None, "max_dsdf": None}
+        if keys_equal:
+            out["weights_equal"] = bool((got[:, 1].float() == ref.weights[order, 0]).all())
+            out["max_dfeat"] = float((got[:, 2:10].float() - ref.features[order]).abs().max())
+            out["max_dsdf"] = float((got[:, 10:].float() - rsdf[order]).abs().max())
+        out["ok"] = bool(keys_equal and out["weights_equal"] and out["max_dfeat"] <= 5e-5 and out["max_dsdf"] <= 1e-4)
+        del ref
+    del vol
+    return out
+
+
 # --------------------------------------------------------------------------------------------- #
 def run_b200(args):
     import torch
@@ -227,16 +285,16 @@ def run_b200(args):
     sampler.start()
     launches0 = lib.bnv_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    enc_ms, fin_ms, rows_total, touched_total, kept_total = [], [], 0, 0, 0
+    enc_ms, fin_ms, pre_ms, rows_total, touched_total, kept_total = [], [], [], 0, 0, 0
     barrier()
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
         step(args.warmup + i)
         ev[i][1].record()
-        a, b = C.c_float(), C.c_float()
-        _lib.check(lib.bnv_map_get_timing(vol._handle, C.byref(a), C.byref(b)), "timing")
-        enc_ms.append(a.value); fin_ms.append(b.value)
+        ms3 = (C.c_float * 3)()
+        _lib.check(lib.bnv_map_get_timing_stages(vol._handle, ms3), "timing")
+        pre_ms.append(ms3[0]); enc_ms.append(ms3[1]); fin_ms.append(ms3[2])
         st = stats.tolist()
         rows_total += int(st[1]); touched_total += int(st[2]); kept_total += int(st[3])
     barrier()
@@ -346,6 +404,9 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, args.brick_log2, args.exchange)
     n_q_job, dec_ms_job = n_q, dec_ms
     if world > 1:      # whole-job decode: every rank decodes its own voxels; halo copies do not count
         own = int(shard.owned_rows().sum())
@@ -357,6 +418,7 @@ def run_b200(args):
     enc_avg = float(np.mean(enc_ms))
     rows_per_launch = rows_total / args.steps
     enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
+    pre_avg, fin_avg = float(np.mean(pre_ms)), float(np.mean(fin_ms))
     scatter_bytes = 2 * H * W + 64 + touched_total / args.steps * 44 + kept_total / args.steps * 80
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -395,22 +457,24 @@ def run_b200(args):
                                     "integration at 2.5 cm, host depth in, frame stats out"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "encode (fused backproject + 8-corner MLP + scatter)", "bound": "tensor",
+            "roofline": {"kernel": "encode_chain_kernel (8 corner rows per point record -> encoder MLP on tcgen05 -> scatter-add)"
+                                   if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel (fp32 CUDA cores)",
+                         "bound": "tensor",
                          "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                          "frac": enc_tflops / pk["tf_burst"],
-                         "traffic": traffic("encode_tc_kernel" if config.mlp_mode_name() == "tc16" else "encode_simt_kernel"),
+                         "traffic": traffic("encode_chain_kernel" if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
                          "peak_source": pk["src"],
-                         "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "finalize_ms": float(np.mean(fin_ms))},
-            # the scatter stage is "HBM-bound by contract"; with ~10 MB of algorithmic traffic per frame
-            # it is nowhere near the HBM roof (latency / L2-atomic bound), reported for completeness
-            "roofline_hbm": {"kernel": "encode + finalize (scatter / upsert stage)", "bound": "hbm",
-                             "achieved": scatter_bytes / ((enc_avg + float(np.mean(fin_ms))) * 1e-3) / 1e9,
+                         "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "prepass_ms": pre_avg, "finalize_ms": fin_avg},
+            # the scatter stage is "HBM-bound by contract": the prepass (depth in, claims + counts, point
+            # records out) and finalize (scratch rows in, map upsert) kernels carry all of the frame's algorithmic bytes
+            "roofline_hbm": {"kernel": "frame_prepass_kernel + finalize_fused_kernel (scatter / upsert stage)", "bound": "hbm",
+                             "achieved": scatter_bytes / ((pre_avg + fin_avg) * 1e-3) / 1e9,
                              "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": scatter_bytes / ((enc_avg + float(np.mean(fin_ms))) * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "frac": scatter_bytes / ((pre_avg + fin_avg) * 1e-3) / 1e9 / pk["hbm_gbs"],
                              "algorithmic_bytes_per_launch": scatter_bytes,
-                             "traffic": traffic("encode_tc_kernel" if config.mlp_mode_name() == "tc16" else "encode_simt_kernel"),
+                             "traffic": ((traffic("frame_prepass_kernel") or 0) + (traffic("finalize_fused_kernel") or 0)) or None,
                              "note": "bytes = 2*H*W (uint16 depth) + 64 + M_t*44 + M*80 (SURVEY 8d with the uint16 depth "
-                                     "image this path reads); M_t, M from the frame statistics"},
+                                     "image this path reads); M_t, M from the frame statistics; time = prepass + finalize"},
             "decode": {"value": n_q_job / (dec_ms_job * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_q_job,
                        "active_voxels_rank0": A, "ms": dec_ms_job,
                        "path": "bnv_decode_voxel_blocks (meshlize samples): G[voxel][offset] table on the tensor cores + blend",
@@ -433,7 +497,14 @@ def run_b200(args):
                                                 "traffic": traffic("decode_tc_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel")}}},
             "cpu_baseline": cpu,
         }
+        if parity is not None:
+            out["shard_parity"] = parity
         print(json.dumps(out))
+        if parity is not None and not parity["ok"]:
+            print("shard_parity FAILED: the tile-sharded map differs from the single-GPU map", file=sys.stderr)
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(1)
     if world > 1:
         dist.destroy_process_group()
 
@@ -531,6 +602,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,
                     help="opt-in: BASELINE configs[4] paced ARKit-shape stream (e.g. 60), prints latency percentiles instead")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],

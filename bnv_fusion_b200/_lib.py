@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbnv_b200.so")
+# BNV_LIB: profiling builds only (tools/chain_phase_profile.py loads the -DBNV_CHAIN_PROFILE=1 variant)
+LIB_PATH = os.environ.get("BNV_LIB") or os.path.join(_HERE, "libbnv_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MLP_FP32 = 0
@@ -50,6 +51,7 @@ SIGNATURES = {
     "bnv_tsdf_prior": (C.c_int, [_P, C.c_double, C.c_double, _P, _P]),
     "bnv_map_set_timing": (C.c_int, [_P, C.c_int]),
     "bnv_map_get_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "bnv_map_get_timing_stages": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "bnv_map_set_halo_buffer": (C.c_int, [_P, _P, _I64]),
     "bnv_map_halo_begin": (C.c_int, [_P, _P]),
     "bnv_map_insert_halo": (C.c_int, [_P, _P, C.c_int, _I64, _P]),

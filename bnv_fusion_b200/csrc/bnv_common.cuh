@@ -60,14 +60,18 @@ struct MapDev {
   float* weights;       // [cap]
   float* hits;          // [cap]
   int32_t cap;
-  // per-frame scratch: flat id -> scratch row (the first (point,corner) row that touched the voxel)
-  int32_t* ftable;      // [n_vox]
-  int32_t* fkeys;       // [fcap]
-  long long* fsum;      // [fcap, 8] 2^30 fixed-point sums (order-independent => deterministic)
-  int32_t* fcnt;        // [fcap]
-  int32_t* touched;     // [fcap] scratch rows in first-touch order
-  int32_t fcap;
-  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter
+  // per-frame scratch.  ftable[flat] is ONE 64-bit word per grid cell: low 32 bits = rows (point, corner) that
+  // fell into the voxel this frame -- the exact integer count of scatter_mean, and the claim at the same time: the
+  // row whose atomicAdd returns count 0 touched the voxel first -- high 32 bits = the voxel's dense scratch row,
+  // allocated by that first row from ctr[1].  Scratch rows are therefore contiguous in first-touch order
+  // (fkeys / fsum rows [0, n_touched)), finalize streams them and zeroes the table entries it visits.
+  unsigned long long* ftable;  // [n_vox]
+  int32_t* fkeys;       // [fcap] flat id of scratch row
+  long long* fsum;      // [fcap, 8] 2^30 fixed-point int64 sums (exact-parity mode: order-independent => deterministic);
+                        // the tensor-core mode uses the same buffer as float [fcap, 8]
+  float* prec;          // [max_points, 8] compacted in-bounds point records of the frame: voxel-space xyz, normal, pad
+  int32_t fcap;         // min(8 * max_points, n_vox)
+  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter, [4] n point records
   int32_t* ctr;
   // halo buffer of the tile shard (nullable): [int32 count, pad[9], records of 10 x 4 B]
   int32_t* halo;
@@ -132,7 +136,7 @@ struct bnv_map {
   void* gtable;         // [(cap + 1) x 27] float: G[V][l] of the factored meshlize decode
   size_t gtable_bytes;
   int timing;           // bnv_map_set_timing
-  cudaEvent_t ev[3];    // before encode / after encode / after finalize
+  cudaEvent_t ev[4];    // before the prepass / after the MLP kernel / after finalize / after the prepass
 };
 
 struct bnv_mlp {

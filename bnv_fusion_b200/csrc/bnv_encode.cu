@@ -10,17 +10,24 @@
 //   torch.unique + torch_scatter.scatter_mean       (local_point_fusion.py:118-126)
 //   src/models/fusion/local_point_fusion.py:647-673 (_update / _integrate)
 //
-// Design: no sort and no per-row temporaries.  Every (point, corner) row looks its voxel up in the
-// per-frame identity table `ftable`; the first row to touch a voxel claims it with ONE atomicCAS
-// whose payload is the row's own index -- that index doubles as the voxel's scratch row, so no slot
-// allocator and no spinning are needed (the scratch arrays are as long as the frame's row count;
-// HBM capacity makes that free).  Features are accumulated as 2^30 fixed-point int64 atomics:
-// integer addition is associative, so the per-voxel mean is bit-reproducible regardless of the
-// order in which warps arrive (the reference's fp16 atomics are not).
+// Design: no sort and no per-row temporaries; three stream-ordered kernels per frame.
+//   1. frame_prepass_kernel (full occupancy, latency-bound work): back-projection in float64, bound mask (A1),
+//      voxel coordinates (A2), and for every (point, corner) row ONE 64-bit atomicAdd on the per-frame table
+//      ftable[flat]: it counts the row (scatter_mean's exact integer count) and, when it returns 0, makes the row
+//      the voxel's first toucher, which allocates the voxel's dense scratch row.  Runs of neighbouring pixels that
+//      fall into the same voxel are merged by warp shuffle before the atomic (one add of the run length).  The
+//      in-bounds points are compacted into 32-byte records (voxel-space xyz + normal).
+//   2. the MLP kernel over the compacted records -- tcgen05 chain (bnv_tc_chain.cu) or fp32 CUDA cores
+//      (encode_rows_simt_kernel below): 8 corner rows per point, features reduced into the dense scratch rows.
+//   3. finalize_fused_kernel: streams the dense scratch rows (mean, count filter, running average into the
+//      persistent map) and re-arms the table entries it visited.
+// Exact-parity mode accumulates 2^30 fixed-point int64 sums: integer addition is associative, so the per-voxel
+// mean is bit-reproducible regardless of the order in which warps arrive (the reference's fp16 atomics are not).
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "bnv_common.cuh"
+#include "bnv_decode_common.cuh"
 #include "bnv_frame.cuh"
 #include "bnv_mlp_simt.cuh"
 
@@ -54,86 +61,188 @@ __global__ void compact_pts_kernel(const float* __restrict__ pts, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------- //
-// encode: one thread per point, 8 corner rows each
+// 1. prepass: back-project, bound mask, claim + count every (point, corner) row, compact the points
+// ------------------------------------------------------------------------------------------- //
+constexpr int kPreThreads = kTileW * kTileH;   // 256: one 32 x 8 pixel tile (a warp = 32 pixels of one image row)
+
+template <bool FROM_DEPTH>
+__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats) {
+  __shared__ FrameTile tile;
+  __shared__ int s_new[kPreThreads / 32], s_keep[kPreThreads / 32], s_stat[3], s_base[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const GeomDev& g = m.g;
+  if (tid < 3) s_stat[tid] = 0;
+  float p[6];
+  bool valid = false;
+  int32_t pix = 0;
+  if (FROM_DEPTH) {
+    const int tiles_x = (src.cam.W + kTileW - 1) / kTileW;
+    const int u0 = (blockIdx.x % tiles_x) * kTileW, v0 = (blockIdx.x / tiles_x) * kTileH;
+    stage_frame_tile(tile, src.depth, src.cam, src.zlut, u0, v0);
+    __syncthreads();
+    const int u = u0 + lane, v = v0 + warp;
+    pix = v * src.cam.W + u;
+    if (u < src.cam.W && v < src.cam.H) valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
+  } else {
+    const int64_t idx = (int64_t)blockIdx.x * kPreThreads + tid;
+    pix = (int32_t)idx;
+    if (idx < src.n_points) {
+      valid = true;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
+    }
+    __syncthreads();
+  }
+  // rule A1 (local_point_fusion.py:94-100): strict bounds one voxel inside the volume
+  bool inb = valid;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) inb = inb && (p[a] < g.hi[a]) && (p[a] > g.lo[a]);
+  float c[3], fl[3], ce[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    c[a] = inb ? __fmul_rn(__fsub_rn(p[a], g.bmin[a]), g.inv_vs) : 0.f;   // rule A2
+    fl[a] = floorf(c[a]);
+    ce[a] = ceilf(c[a]);
+  }
+  // ---- one 64-bit atomicAdd per run of lanes whose corner k is the same owned voxel ------------------------
+  unsigned long long old[8];
+  int32_t key[8];
+  uint32_t own = 0, issued = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float nb[3];
+    corner_of(k, fl, ce, nb);                                            // rule A3 (modules.py:178-247)
+    const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
+    const bool o = inb && owns(g, ix, iy, iz);
+    key[k] = o ? ix * g.nyz + iy * g.n[2] + iz : -1 - lane;              // rule A5 (int32); negatives never merge
+    own |= (o ? 1u : 0u) << k;
+    const int32_t prev = __shfl_up_sync(0xffffffffu, key[k], 1);
+    const bool head = lane == 0 || prev != key[k];
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    old[k] = 1;
+    if (head && o) {
+      const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
+      const int run = rest ? __ffs(rest) : 32 - lane;
+      old[k] = atomicAdd(&m.ftable[key[k]], (unsigned long long)run);
+      issued |= 1u << k;
+    }
+  }
+  // ---- first touchers allocate dense scratch rows; in-bounds points get a record slot ---------------------
+  uint32_t win = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (((issued >> k) & 1u) && ft_count(old[k]) == 0) win |= 1u << k;
+  const int n_new = __popc(win);
+  int incl = n_new;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const bool keep = own != 0;
+  const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+  const uint32_t vb = __ballot_sync(0xffffffffu, valid), ib = __ballot_sync(0xffffffffu, inb);
+  int rows = __popc(own);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+  if (lane == 31) s_new[warp] = incl;
+  if (lane == 0) {
+    s_keep[warp] = __popc(kb);
+    if (vb) atomicAdd(&s_stat[0], __popc(vb));
+    if (rows) atomicAdd(&s_stat[1], rows);
+    if (ib) atomicAdd(&s_stat[2], __popc(ib));
+  }
+  __syncthreads();
+  if (lane == 0 && warp < 3) {       // three warps: the two allocations and the statistics go out in parallel
+    if (warp == 0) {
+      int t = 0;
+      for (int w = 0; w < kPreThreads / 32; ++w) t += s_new[w];
+      s_base[0] = t ? atomicAdd(&m.ctr[1], t) : 0;
+    } else if (warp == 1) {
+      int t = 0;
+      for (int w = 0; w < kPreThreads / 32; ++w) t += s_keep[w];
+      s_base[1] = t ? atomicAdd(&m.ctr[4], t) : 0;
+    } else {
+      if (s_stat[0]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)s_stat[0]);
+      if (s_stat[1]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)s_stat[1]);
+      if (s_stat[2]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)s_stat[2]);
+    }
+  }
+  __syncthreads();
+  int row = s_base[0] + incl - n_new, rec = s_base[1] + __popc(kb & ((1u << lane) - 1u));
+  for (int w = 0; w < warp; ++w) {
+    row += s_new[w];
+    rec += s_keep[w];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if ((win >> k) & 1u) {
+      // publish the dense row in the entry's high word (visible to the kernels that follow) and its key
+      atomicAdd(&m.ftable[key[k]], (unsigned long long)(uint32_t)row << 32);
+      m.fkeys[row] = key[k];
+      ++row;
+    }
+  if (keep) {
+    float4* r4 = reinterpret_cast<float4*>(m.prec + (size_t)rec * 8);
+    r4[0] = make_float4(c[0], c[1], c[2], p[3]);
+    r4[1] = make_float4(p[4], p[5], __int_as_float((int)own), __int_as_float(pix));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- //
+// 2. exact-parity mode: encoder MLP on the CUDA cores, one thread per point record, 8 corner rows each
 // ------------------------------------------------------------------------------------------- //
 using EncMlp = SimtMlp<6, 8>;
 constexpr int kEncThreads = 256;
 constexpr size_t kEncSmem = (size_t)(EncMlp::kFloats + 64 * kEncThreads) * sizeof(float);
 
-template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kEncThreads) encode_simt_kernel(MapDev m, EncSrc src, const float* __restrict__ gW,
-                                                                  long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kEncThreads) encode_rows_simt_kernel(MapDev m, const float* __restrict__ gW) {
   extern __shared__ __align__(16) float smem[];
   float* sW = smem;
   float* sH = smem + EncMlp::kFloats + threadIdx.x;
   load_weights(sW, gW, EncMlp::kFloats);
-  const int64_t idx = (int64_t)blockIdx.x * kEncThreads + threadIdx.x;
-  float p[6];
-  bool valid = false;
-  if (FROM_DEPTH) {
-    if (idx < (int64_t)src.cam.H * src.cam.W)
-      valid = backproject_pixel(src.depth, src.cam, (int)(idx % src.cam.W), (int)(idx / src.cam.W), p);
-  } else if (idx < src.n_points) {
-    valid = true;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
-  }
+  const int n_rec = m.ctr[4];
   const GeomDev& g = m.g;
-  // rule A1 (local_point_fusion.py:94-100): strict bounds one voxel inside the volume
-  bool inb = valid;
+  for (int64_t idx = (int64_t)blockIdx.x * kEncThreads + threadIdx.x; idx < n_rec; idx += (int64_t)gridDim.x * kEncThreads) {
+    const float4* r4 = reinterpret_cast<const float4*>(m.prec + (size_t)idx * 8);
+    const float4 a = __ldg(r4), b = __ldg(r4 + 1);
+    const float c[3] = {a.x, a.y, a.z}, nrm[3] = {a.w, b.x, b.y};
+    const uint32_t own = (uint32_t)__float_as_int(b.z);
+    float fl[3], ce[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) inb = inb && (p[a] < g.hi[a]) && (p[a] > g.lo[a]);
-  int n_rows = 0;
-  if (inb) {
-    float c[3], fl[3], ce[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      c[a] = __fmul_rn(__fsub_rn(p[a], g.bmin[a]), g.inv_vs);   // rule A2
-      fl[a] = floorf(c[a]);
-      ce[a] = ceilf(c[a]);
+    for (int ax = 0; ax < 3; ++ax) {
+      fl[ax] = floorf(c[ax]);
+      ce[ax] = ceilf(c[ax]);
     }
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
-      // corner order of get_neighbors (modules.py:178-247)
-      const int cx = (k == 1 || k == 4 || k == 5 || k == 7);
-      const int cy = (k == 2 || k == 4 || k == 6 || k == 7);
-      const int cz = (k == 3 || k == 5 || k == 6 || k == 7);
-      const float nb[3] = {cx ? ce[0] : fl[0], cy ? ce[1] : fl[1], cz ? ce[2] : fl[2]};
-      const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-      if (!owns(g, ix, iy, iz)) continue;
+      if (!((own >> k) & 1u)) continue;
+      float nb[3];
+      corner_of(k, fl, ce, nb);
       float x[6], y[8];
 #pragma unroll
-      for (int a = 0; a < 3; ++a) {
-        const float rel_n = __fsub_rn(c[a], nb[a]);              // rule A4
+      for (int ax = 0; ax < 3; ++ax) {
+        const float rel_n = __fsub_rn(c[ax], nb[ax]);              // rule A4
         const float rel = __fmul_rn(rel_n, g.vs);
-        x[a] = __fmul_rn(rel, g.inv_vs);
-        x[3 + a] = p[3 + a];
+        x[ax] = __fmul_rn(rel, g.inv_vs);
+        x[3 + ax] = nrm[ax];
       }
       EncMlp::run(sW, sH, kEncThreads, x, y);
-      const int32_t flat = ix * g.nyz + iy * g.n[2] + iz;       // rule A5 (int32)
-      scatter_row(m, flat, (int32_t)(idx * 8 + k), y);
-      ++n_rows;
+      add_row_fixed(m, scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]), y);
     }
-  }
-  // frame statistics: valid pixels / in-bounds points / rows
-  const unsigned mv = __ballot_sync(0xffffffffu, valid);
-  const unsigned mi = __ballot_sync(0xffffffffu, inb);
-  int r = n_rows;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-  if ((threadIdx.x & 31) == 0 && (mv | mi)) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)__popc(mv));
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)r);
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)__popc(mi));
   }
 }
 
 // mean of a scratch row (scatter_mean, local_point_fusion.py:125)
 __device__ __forceinline__ float scratch_mean(const MapDev& m, int32_t row, int j, int32_t cnt, bool f32acc) {
   if (f32acc)   // tensor-core mode: fp32 partial sums (add_row_f32)
-    return (float)((double)reinterpret_cast<const float*>(m.fsum + (size_t)row * kFeat)[j] / (double)cnt);
+    return (float)((double)reinterpret_cast<const float*>(m.fsum)[(size_t)row * kFeat + j] / (double)cnt);
   const long long s = m.fsum[(size_t)row * kFeat + j];
   return (float)(((double)s / kFixScale) / (double)cnt);
+}
+__device__ __forceinline__ void scratch_clear(const MapDev& m, int32_t row, int j, bool f32acc) {
+  if (f32acc) reinterpret_cast<float*>(m.fsum)[(size_t)row * kFeat + j] = 0.f;
+  else m.fsum[(size_t)row * kFeat + j] = 0;
 }
 
 // _update (local_point_fusion.py:647-651), separately rounded like the reference's torch kernels
@@ -141,8 +250,8 @@ __device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new
   return __fdiv_rn(__fadd_rn(__fmul_rn(f_old, w_old), __fmul_rn(f_new, w_new)), w);
 }
 
-// finalize of the fused path: for every voxel touched this frame -> mean, count filter, running
-// average into the persistent map; clears the scratch.  8 lanes per voxel (one feature each).
+// 3. finalize of the fused path: for every voxel touched this frame (dense scratch rows [0, n_touched)) -> mean,
+// count filter, running average into the persistent map; clears the scratch.  8 lanes per voxel (one feature each).
 __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, bool f32acc, long long* __restrict__ stats,
                                                              long long* __restrict__ user_stats,
                                                              float* __restrict__ user_navg) {
@@ -152,11 +261,11 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
   int integrated = 0;
   for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_touched;
        t += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    const int32_t row = m.touched[t];
+    const int32_t row = (int32_t)t;
     const int32_t key = m.fkeys[row];
-    const int32_t cnt = m.fcnt[row];
+    const int32_t cnt = ft_count(m.ftable[key]);
     const float mean = scratch_mean(m, row, lane8, cnt, f32acc);
-    m.fsum[(size_t)row * kFeat + lane8] = 0;
+    scratch_clear(m, row, lane8, f32acc);
     if (cnt >= min_pts) {                                         // local_point_fusion.py:143-147
       int32_t slot = 0;
       if (lane8 == 0) {
@@ -208,10 +317,8 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
         }
       }
     }
-    if (lane8 == 0) {
-      m.ftable[key] = kEmpty;
-      m.fcnt[row] = 0;
-    }
+    __syncwarp(gmask);
+    if (lane8 == 0) m.ftable[key] = 0ull;
   }
   // one statistics atomic per block (same-address atomics serialise in L2)
   __shared__ int s_integrated;
@@ -241,6 +348,7 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
     stats[0] = stats[1] = stats[3] = stats[4] = 0;
     m.ctr[1] = 0;
     m.ctr[3] = 0;
+    m.ctr[4] = 0;
   }
 }
 
@@ -248,16 +356,15 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
 __global__ void sort_prep_kernel(MapDev m, int n, int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  const int32_t row = m.touched[t];
-  keys[t] = m.fkeys[row];
-  vals[t] = row;
+  keys[t] = m.fkeys[t];
+  vals[t] = t;
 }
 
-__global__ void sort_flag_kernel(MapDev m, int n, const int32_t* __restrict__ rows, int min_pts,
+__global__ void sort_flag_kernel(MapDev m, int n, const int32_t* __restrict__ keys, int min_pts,
                                  int32_t* __restrict__ flags) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  flags[t] = m.fcnt[rows[t]] >= min_pts ? 1 : 0;
+  flags[t] = ft_count(m.ftable[keys[t]]) >= min_pts ? 1 : 0;
 }
 
 __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ keys, const int32_t* __restrict__ rows,
@@ -270,9 +377,9 @@ __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ ke
   if (t >= n) return;
   const int32_t row = rows[t];
   const int32_t key = keys[t];
-  const int32_t cnt = m.fcnt[row];
+  const int32_t cnt = ft_count(m.ftable[key]);
   const float mean = scratch_mean(m, row, j, cnt, f32acc);
-  m.fsum[(size_t)row * kFeat + j] = 0;
+  scratch_clear(m, row, j, f32acc);
   if (flags[t]) {
     const int64_t o = scan[t];
     if (o < out_cap) {
@@ -292,10 +399,7 @@ __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ ke
     }
   }
   __syncwarp(0xFFu << ((threadIdx.x & 31) & ~7));
-  if (j == 0) {
-    m.ftable[key] = kEmpty;
-    m.fcnt[row] = 0;
-  }
+  if (j == 0) m.ftable[key] = 0ull;
 }
 
 __global__ void sort_publish_kernel(MapDev m, int n, const int32_t* __restrict__ flags, const int32_t* __restrict__ scan,
@@ -307,6 +411,7 @@ __global__ void sort_publish_kernel(MapDev m, int n, const int32_t* __restrict__
   if (user_navg) *user_navg = n > 0 ? (float)((double)stats[1] / (double)n) : 0.f;
   stats[0] = stats[1] = stats[3] = stats[4] = 0;
   m.ctr[1] = 0;
+  m.ctr[4] = 0;
 }
 
 // _integrate (local_point_fusion.py:653-673) on explicit arrays: 8 lanes per voxel
@@ -375,32 +480,38 @@ using namespace bnv;
 
 // defined in bnv_mlp.cu / bnv_tc.cu
 const float* bnv_internal_simt_weights(const bnv_mlp_t* mlp);
-int bnv_internal_encode_tc(bnv_map_t* map, const void* src, int from_depth, int64_t n_threads,
-                           const bnv_mlp_t* enc, cudaStream_t s);
+int bnv_internal_encode_tc(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
 
 namespace bnv {
+// kernels 1 + 2 of the frame: prepass over `n_threads` pixels / points, then the encoder MLP over the records
 static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int64_t n_threads,
                          const bnv_mlp_t* enc, int mode, cudaStream_t s) {
   if (!enc || enc->n_in != 6 || enc->n_out != 8) { set_error("encode: encoder MLP must be 6 -> 8"); return BNV_E_ARG; }
+  if (mode != BNV_MLP_FP32 && mode != BNV_MLP_TC16) { set_error("encode: unknown MLP mode %d", mode); return BNV_E_ARG; }
   if (n_threads > map->max_points) {
     set_error("encode: %lld points exceed the map's max_points %lld", (long long)n_threads, (long long)map->max_points);
     return BNV_E_CAPACITY;
   }
   if (n_threads == 0) return BNV_OK;
-  if (mode == BNV_MLP_TC16) return bnv_internal_encode_tc(map, &src, from_depth ? 1 : 0, n_threads, enc, s);
-  if (mode != BNV_MLP_FP32) { set_error("encode: unknown MLP mode %d", mode); return BNV_E_ARG; }
-  const unsigned blocks = (unsigned)((n_threads + kEncThreads - 1) / kEncThreads);
-  const float* gW = bnv_internal_simt_weights(enc);
   if (from_depth) {
-    static bool attr = false;
-    if (!attr) { BNV_CUDA(cudaFuncSetAttribute(encode_simt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem)); attr = true; }
-    encode_simt_kernel<true><<<blocks, kEncThreads, kEncSmem, s>>>(map->d, src, gW, (long long*)map->stats);
+    const unsigned tiles = (unsigned)(((src.cam.W + kTileW - 1) / kTileW) * ((src.cam.H + kTileH - 1) / kTileH));
+    frame_prepass_kernel<true><<<tiles, kPreThreads, 0, s>>>(map->d, src, (long long*)map->stats);
   } else {
-    static bool attr = false;
-    if (!attr) { BNV_CUDA(cudaFuncSetAttribute(encode_simt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem)); attr = true; }
-    encode_simt_kernel<false><<<blocks, kEncThreads, kEncSmem, s>>>(map->d, src, gW, (long long*)map->stats);
+    frame_prepass_kernel<false><<<(unsigned)((n_threads + kPreThreads - 1) / kPreThreads), kPreThreads, 0, s>>>(
+        map->d, src, (long long*)map->stats);
   }
-  BNV_LAUNCH_CHECK("encode_simt_kernel");
+  BNV_LAUNCH_CHECK("frame_prepass_kernel");
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[3], s));
+  if (mode == BNV_MLP_TC16) return bnv_internal_encode_tc(map, n_threads, enc, s);
+  static bool attr[64] = {false};            // cudaFuncSetAttribute is per device
+  if (!attr[map->device & 63]) {
+    BNV_CUDA(cudaFuncSetAttribute(encode_rows_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem));
+    attr[map->device & 63] = true;
+  }
+  const int64_t blocks = (n_threads + kEncThreads - 1) / kEncThreads;
+  encode_rows_simt_kernel<<<(unsigned)(blocks < 148 * 2 ? blocks : 148 * 2), kEncThreads, kEncSmem, s>>>(
+      map->d, bnv_internal_simt_weights(enc));
+  BNV_LAUNCH_CHECK("encode_rows_simt_kernel");
   return BNV_OK;
 }
 
@@ -470,11 +581,11 @@ int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_host, int H, int W
     }
   }
   const int cur = map->stage_next;
-  if (map->prefetched == depth_host && map->prefetched_bytes == bytes) {
-    BNV_CUDA(cudaStreamWaitEvent(s, map->stage_ready[cur], 0));        // hinted at the previous call: copy in flight / done
-  } else {
+  // a prefetch hinted at the previous call targets depth_stage[cur]: whether or not it is the frame passed now,
+  // nothing on `s` may read or overwrite that buffer before the copy stream's write has landed
+  if (map->prefetched) BNV_CUDA(cudaStreamWaitEvent(s, map->stage_ready[cur], 0));
+  if (!(map->prefetched == depth_host && map->prefetched_bytes == bytes))
     BNV_CUDA(cudaMemcpyAsync(map->depth_stage[cur], depth_host, bytes, cudaMemcpyHostToDevice, s));
-  }
   int rc = bnv_fuse_frame(map, map->depth_stage[cur], H, W, K, T, max_depth, enc, min_pts, mode,
                           frame_stats_host ? map->user_stats : nullptr, nullptr, stream);
   if (rc) return rc;
@@ -540,7 +651,7 @@ int bnv_encode_points(bnv_map_t* map, const float* pts6, int64_t n_points, const
     BNV_CUDA(cub::DeviceRadixSort::SortPairs(map->cub_tmp, tmp, map->sort_keys_in, map->sort_keys_out,
                                              map->sort_vals_in, map->sort_vals_out, n, 0, end_bit, s));
     count_launch(4);
-    sort_flag_kernel<<<nb, 256, 0, s>>>(map->d, n, map->sort_vals_out, min_pts, map->flags);
+    sort_flag_kernel<<<nb, 256, 0, s>>>(map->d, n, map->sort_keys_out, min_pts, map->flags);
     BNV_LAUNCH_CHECK("sort_flag_kernel");
     tmp = map->cub_tmp_bytes;
     BNV_CUDA(cub::DeviceScan::ExclusiveSum(map->cub_tmp, tmp, map->flags, map->scan, n, s));

@@ -269,20 +269,19 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   g.rank = 0; g.world = 1; g.brick_log2 = 4;
   MapDev& d = m->d;
   d.cap = (int32_t)capacity;
-  d.fcap = (int32_t)(max_points * 8);
+  d.fcap = (int32_t)(max_points * 8 < g.n_vox ? max_points * 8 : g.n_vox);   // a frame cannot touch more voxels
   const int64_t aux = d.cap > d.fcap ? d.cap : d.fcap;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   alloc((void**)&d.table, g.n_vox * 4);
-  alloc((void**)&d.ftable, g.n_vox * 4);
+  alloc((void**)&d.ftable, g.n_vox * 8);
   alloc((void**)&d.keys, (size_t)d.cap * 4);
   alloc((void**)&d.feats, (size_t)d.cap * kFeat * 4);
   alloc((void**)&d.weights, (size_t)d.cap * 4);
   alloc((void**)&d.hits, (size_t)d.cap * 4);
   alloc((void**)&d.fkeys, (size_t)d.fcap * 4);
   alloc((void**)&d.fsum, (size_t)d.fcap * kFeat * 8);
-  alloc((void**)&d.fcnt, (size_t)d.fcap * 4);
-  alloc((void**)&d.touched, (size_t)d.fcap * 4);
+  alloc((void**)&d.prec, (size_t)max_points * 8 * 4);
   alloc((void**)&d.ctr, 16 * 4);
   alloc((void**)&m->sort_keys_in, (size_t)d.fcap * 4);
   alloc((void**)&m->sort_keys_out, (size_t)d.fcap * 4);
@@ -312,11 +311,9 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   int rc = bnv_map_reset(m, nullptr);
   if (rc != BNV_OK) return rc;
   BNV_CUDA(cudaMemsetAsync(d.fsum, 0, (size_t)d.fcap * kFeat * 8, 0));
-  BNV_CUDA(cudaMemsetAsync(d.fcnt, 0, (size_t)d.fcap * 4, 0));
   BNV_CUDA(cudaMemsetAsync(m->flags, 0, (size_t)aux * 4, 0));
   BNV_CUDA(cudaMemsetAsync(m->stats, 0, 64, 0));
-  rc = fill_i32(d.ftable, g.n_vox, kEmpty, 0);
-  if (rc != BNV_OK) return rc;
+  BNV_CUDA(cudaMemsetAsync(d.ftable, 0, (size_t)g.n_vox * 8, 0));
   zlut_kernel<<<256, 256>>>(m->zlut);
   BNV_LAUNCH_CHECK("zlut_kernel");
   BNV_CUDA(cudaStreamSynchronize(0));
@@ -327,12 +324,12 @@ int bnv_map_destroy(bnv_map_t* m) {
   if (!m) return BNV_OK;
   cudaSetDevice(m->device);
   MapDev& d = m->d;
-  void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.fcnt,
-                  d.touched, d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
+  void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.prec,
+                  d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
                   m->sort_vals_out, m->flags, m->scan, m->zlut, m->depth_stage[0], m->depth_stage[1], m->user_stats, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
-  for (int i = 0; i < 3; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
+  for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);
   for (int i = 0; i < 2; ++i) {
     if (m->stage_ready[i]) cudaEventDestroy(m->stage_ready[i]);
     if (m->stage_free[i]) cudaEventDestroy(m->stage_free[i]);
@@ -385,7 +382,7 @@ int bnv_map_set_timing(bnv_map_t* m, int enable) {
   if (!m) { set_error("bnv_map_set_timing: null map"); return BNV_E_ARG; }
   BNV_CUDA(cudaSetDevice(m->device));
   if (enable && !m->ev[0])
-    for (int i = 0; i < 3; ++i) BNV_CUDA(cudaEventCreate(&m->ev[i]));
+    for (int i = 0; i < 4; ++i) BNV_CUDA(cudaEventCreate(&m->ev[i]));
   m->timing = enable ? 1 : 0;
   return BNV_OK;
 }
@@ -395,6 +392,15 @@ int bnv_map_get_timing(bnv_map_t* m, float* enc_ms, float* fin_ms) {
   BNV_CUDA(cudaEventSynchronize(m->ev[2]));
   BNV_CUDA(cudaEventElapsedTime(enc_ms, m->ev[0], m->ev[1]));
   BNV_CUDA(cudaEventElapsedTime(fin_ms, m->ev[1], m->ev[2]));
+  return BNV_OK;
+}
+
+int bnv_map_get_timing_stages(bnv_map_t* m, float* ms3) {
+  if (!m || !m->ev[0] || !ms3) { set_error("bnv_map_get_timing_stages: timing was never enabled"); return BNV_E_ARG; }
+  BNV_CUDA(cudaEventSynchronize(m->ev[2]));
+  BNV_CUDA(cudaEventElapsedTime(ms3 + 0, m->ev[0], m->ev[3]));
+  BNV_CUDA(cudaEventElapsedTime(ms3 + 1, m->ev[3], m->ev[1]));
+  BNV_CUDA(cudaEventElapsedTime(ms3 + 2, m->ev[1], m->ev[2]));
   return BNV_OK;
 }
 

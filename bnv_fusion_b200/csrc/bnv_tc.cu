@@ -127,8 +127,7 @@ int bnv_internal_pack_tc_weights(bnv_mlp_t* mlp, const float* params) {
 
 // chain kernels (bnv_tc_chain.cu)
 int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s);
-int bnv_internal_encode_chain(bnv_map_t* map, const void* srcp, int from_depth, int64_t n_threads, const bnv_mlp_t* enc,
-                              cudaStream_t s);
+int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
 int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s);
 int bnv_internal_gtable_chain(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s);
 
@@ -136,9 +135,8 @@ int bnv_internal_mlp_forward_tc(const bnv_mlp_t* mlp, const float* x, int64_t n,
   return bnv_internal_mlp_forward_chain(mlp, x, n, y, s);
 }
 
-int bnv_internal_encode_tc(bnv_map_t* map, const void* srcp, int from_depth, int64_t n_threads, const bnv_mlp_t* enc,
-                           cudaStream_t s) {
-  return bnv_internal_encode_chain(map, srcp, from_depth, n_threads, enc, s);
+int bnv_internal_encode_tc(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s) {
+  return bnv_internal_encode_chain(map, max_records, enc, s);
 }
 
 int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {

@@ -1,13 +1,12 @@
-// tcgen05 kernels on the software-pipelined chain (bnv_tc.cuh): plain MLP forward, fused encode
-// (backproject -> 8 corner rows -> encoder MLP -> scatter), fused decode (8-corner gather -> decoder MLP ->
+// tcgen05 kernels on the software-pipelined chain (bnv_tc.cuh): plain MLP forward, encode
+// (point records -> 8 corner rows -> encoder MLP -> scatter), fused decode (8-corner gather -> decoder MLP ->
 // trilinear blend + prior) and the G table of the factored meshlize decode.
 //
 //  * every item (one 128-row tile through the MLP) costs three exposed MMA round trips: the output layer runs on
 //    the tensor core and is issued together with the next item's first layer, its result is consumed in the
 //    shadow of the next item;
-//  * the encode kernel splits the frame at (tile, corner) granularity: every chain gets the same number of
-//    corner rows (+-1); the claim CAS of a tile are issued in its prologue and settled in the shadow of its
-//    first round;
+//  * the encode kernel runs over the point records the frame prepass compacted (bnv_encode.cu) and splits them at
+//    (tile, corner) granularity: every chain gets the same number of corner rows (+-1);
 //  * in the tile shard, the corners nobody in the warpgroup owns are dropped from the item list up front.
 #include <cuda_fp16.h>
 #include <limits.h>
@@ -131,126 +130,64 @@ __device__ __forceinline__ void enc_input(int k, const float (&cc)[3], const flo
   in[5] = in[6] = in[7] = kOnes;
 }
 
-template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc src, const uint8_t* __restrict__ gW,
-                                                                 int w_bytes, int64_t n_threads,
-                                                                 long long* __restrict__ stats, int debug) {
-  // debug (BNV_DEBUG_ENCODE, profiling ablations only): 1 no MMA chain, 2 no feature reductions,
-  // 4 no claims (+ no reductions), 8 whole tiles per chain instead of the (tile, corner) split
+__global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, const uint8_t* __restrict__ gW, int w_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
   RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5;
   const GeomDev& g = m.g;
-  // (u - cx) / fx and (v - cy) / fy in float64 for every column / row, once per CTA (bnv_frame.cuh)
-  double* s_ax = reinterpret_cast<double*>(weights_smem(smem) + ((w_bytes + 127) / 128) * 128);
-  double* s_ay = s_ax + (FROM_DEPTH ? src.cam.W : 0);
-  if (FROM_DEPTH) {
-    build_ratio_tables(src.cam, s_ax, s_ay);
-    __syncthreads();
-  }
-  const int64_t n_units = ((n_threads + 127) / 128) * 8;
+  const int64_t n_rec = m.ctr[4];                       // point records written by frame_prepass_kernel
+  const int64_t n_units = ((n_rec + 127) / 128) * 8;
   const int64_t chain = (int64_t)blockIdx.x * kNWG + wg, n_chains = (int64_t)gridDim.x * kNWG;
   const int64_t u_end = n_units * (chain + 1) / n_chains;
-  int st_valid = 0, st_inb = 0, st_rows = 0;           // frame statistics, flushed once per warp at the end
-  int32_t pend_slot = -1;
+  int32_t pend_row = -1;
   bool pending = false;                                // an output layer is in flight / unread in D_out
   int flip = 0;
   auto drain = [&]() {
     if (pending) {
       float y[8];
-      if (debug & 1) { for (int j = 0; j < 8; ++j) y[j] = (float)j; } else
       chain_output<8>(c, y);
-      if (debug & 16) { if (!(debug & 6)) add_row_f32_runs(m, pend_slot, y); } else
-      if (pend_slot >= 0 && !(debug & 6)) add_row_f32(m, pend_slot, y);
+      if (pend_row >= 0) add_row_f32(m, pend_row, y);
       pending = false;
     }
   };
-  int64_t u_begin = n_units * chain / n_chains, u_stop = u_end, u_step = 0;
-  if (debug & 8) { u_begin = chain * 8; u_stop = n_units; u_step = (n_chains - 1) * 8; }
-  for (int64_t u = u_begin; u < u_stop; u += u_step) {
+  for (int64_t u = n_units * chain / n_chains; u < u_end;) {
     const int64_t tile = u >> 3;
     const int k0 = (int)(u & 7);
-    const int k1 = (int)(u_stop - u < (int64_t)(8 - k0) ? k0 + (u_stop - u) : 8);
+    const int k1 = (int)(u_end - u < (int64_t)(8 - k0) ? k0 + (u_end - u) : 8);
     u += k1 - k0;
     const int64_t idx = tile * 128 + r;
-    float p[6];
-    bool valid = false;
-    if (FROM_DEPTH) {
-      if (idx < n_threads)
-        valid = backproject_pixel_lut(src.depth, src.cam, src.zlut, s_ax, s_ay, (int)(idx % src.cam.W),
-                                      (int)(idx / src.cam.W), p);
-    } else if (idx < n_threads) {
-      valid = true;
-#pragma unroll
-      for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+    if (idx < n_rec) {
+      const float4* r4 = reinterpret_cast<const float4*>(m.prec + (size_t)idx * 8);
+      ra = __ldg(r4);
+      rb = __ldg(r4 + 1);
     }
-    bool inb = valid;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) inb = inb && (p[a] < g.hi[a]) && (p[a] > g.lo[a]);     // rule A1
-    float cc[3], fl[3], ce[3];
+    const float cc[3] = {ra.x, ra.y, ra.z};
+    float fl[3], ce[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      cc[a] = inb ? __fmul_rn(__fsub_rn(p[a], g.bmin[a]), g.inv_vs) : 0.f;             // rule A2
       fl[a] = floorf(cc[a]);
       ce[a] = ceilf(cc[a]);
     }
-    const uint32_t nrm01 = pack_f16x2(inb ? p[3] : 0.f, inb ? p[4] : 0.f);
-    const uint32_t nrm2o = pack_f16x2(inb ? p[5] : 0.f, 1.f);
-    // claim the scratch rows of this chain's corners: the CAS round trips are only ISSUED here (8 in
-    // flight per thread); their results are consumed in the shadow of the tile's first MLP round
-    // (`settle`), so neither the CAS latency nor the first-touch bookkeeping sits on the chain's critical path
-    int32_t old[8];
-    uint32_t own = 0;
+    const uint32_t nrm01 = pack_f16x2(ra.w, rb.x);
+    const uint32_t nrm2o = pack_f16x2(rb.y, 1.f);
+    // corners of this chain's unit range that this rank owns (the prepass stored the ownership mask)
+    const uint32_t range = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
+    const uint32_t own = (idx < n_rec ? (uint32_t)__float_as_int(rb.z) : 0u) & range;
+    // dense scratch rows of the owned corners: 8 independent table reads in flight (high word of ftable[flat])
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float nb[3];
-      corner_of(k, fl, ce, nb);
-      const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-      old[k] = -2;
-      if (k >= k0 && k < k1 && inb && owns(g, ix, iy, iz)) {
-        own |= 1u << k;
-        old[k] = (debug & 4) ? 0 : atomicCAS(&m.ftable[ix * g.nyz + iy * g.n[2] + iz], kEmpty, (int32_t)(idx * 8 + k));   // rule A5
+      int32_t row = -1;
+      if ((own >> k) & 1u) {
+        float nb[3];
+        corner_of(k, fl, ce, nb);
+        row = scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]);   // rule A5
       }
+      S.slot[k][threadIdx.x] = row;
     }
-    // first-touch bookkeeping of the claimed rows: ONE counter atomic per warp (warp prefix sum)
-    auto settle = [&]() {
-      int n_new = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) n_new += (((own >> k) & 1u) && old[k] == kEmpty) ? 1 : 0;
-      const int lane = threadIdx.x & 31;
-      int incl = n_new;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      int base = 0;
-      if (lane == 31 && incl > 0) base = atomicAdd(&m.ctr[1], incl);
-      int pos = __shfl_sync(0xffffffffu, base, 31) + incl - n_new;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        int32_t sl = -1;
-        if ((own >> k) & 1u) {
-          sl = old[k];
-          if (sl == kEmpty) {
-            float nb[3];
-            corner_of(k, fl, ce, nb);
-            sl = (int32_t)(idx * 8 + k);
-            m.fkeys[sl] = (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2];
-            m.touched[pos++] = sl;
-          }
-        }
-        S.slot[k][threadIdx.x] = sl;
-      }
-    };
-    if (k0 == 0) {
-      st_valid += valid ? 1 : 0;
-      st_inb += inb ? 1 : 0;
-    }
-    st_rows += __popc(own);
     // corners to run: all of [k0, k1) on one GPU; in the tile shard only those somebody here owns
-    uint32_t live = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
+    uint32_t live = range;
     if (g.world > 1) {
       const uint32_t wown = __reduce_or_sync(0xffffffffu, own);
       if ((r & 31) == 0) S.sh.live[wg][flip][warp_in_wg] = wown;
@@ -259,16 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       flip ^= 1;
     }
     if (live == 0) continue;              // nobody here owns anything of this tile: `own` is 0 for every thread
-    if (debug & 1) {                      // ablation: no MMA chain
-      drain();
-      settle();
-      for (uint32_t rem = live; rem; rem &= rem - 1) {
-        drain();
-        pending = true;
-        pend_slot = S.slot[__ffs(rem) - 1][threadIdx.x];
-      }
-      continue;
-    }
     // the chain is idle here (the previous tile's last corner was finished without a next item; its
     // output, if still unread, is drained in the shadow of this tile's first corner)
     {
@@ -277,18 +204,13 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
       chain_stage<8>(c, in);
       chain_begin<8>(c);
     }
-    bool first = true;
 #pragma unroll 1
     for (uint32_t rem = live; rem;) {
       const int k = __ffs(rem) - 1;
       rem &= rem - 1;
       const bool has_next = rem != 0;
       chain_hidden<8>(
-          c,
-          [&]() {
-            drain();
-            if (first) settle();
-          },
+          c, [&]() { drain(); },
           [&]() {
             if (has_next) {
               uint32_t in[8];
@@ -296,24 +218,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_tc_kernel(MapDev m, EncSrc
               chain_stage<8>(c, in);
             }
           });
-      first = false;
       chain_finish<8>(c, has_next);
       pending = true;
-      pend_slot = S.slot[k][threadIdx.x];
+      pend_row = S.slot[k][threadIdx.x];
     }
   }
   drain();
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    st_valid += __shfl_xor_sync(0xffffffffu, st_valid, o);
-    st_inb += __shfl_xor_sync(0xffffffffu, st_inb, o);
-    st_rows += __shfl_xor_sync(0xffffffffu, st_rows, o);
-  }
-  if ((threadIdx.x & 31) == 0 && (st_valid | st_inb | st_rows)) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)st_valid);
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)st_rows);
-    atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)st_inb);
-  }
   tc_teardown<kNWG>(S.sh);
 }
 
@@ -585,28 +495,14 @@ int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t
   return BNV_OK;
 }
 
-int bnv_internal_encode_chain(bnv_map_t* map, const void* srcp, int from_depth, int64_t n_threads, const bnv_mlp_t* enc,
-                            cudaStream_t s) {
-  const EncSrc& src = *reinterpret_cast<const EncSrc*>(srcp);
-  const char* e = getenv("BNV_DEBUG_ENCODE");     // profiling experiments only
-  const int dbg = e ? atoi(e) : 0;
-  const size_t tables = from_depth ? (size_t)(src.cam.W + src.cam.H) * 8 : 0;      // float64 ratio tables of the back-projection
-  // weights (padded to 128 B) + the two float64 ratio tables of the back-projection
-  const size_t smem = ((smem_bytes(enc->in_pad) + 127) / 128) * 128 + tables;
-  if (smem > 200 * 1024) { set_error("encode: image of %d x %d is too large for the shared-memory ratio tables", src.cam.W, src.cam.H); return BNV_E_UNSUPPORTED; }
-  const int grid = grid_for(((n_threads + 127) / 128) * 8);        // units = (tile, corner)
-  if (from_depth) {
-    int rc = set_smem(encode_tc_kernel<true>, smem);
-    if (rc) return rc;
-    encode_tc_kernel<true><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
-                                                         n_threads, (long long*)map->stats, dbg);
-  } else {
-    int rc = set_smem(encode_tc_kernel<false>, smem);
-    if (rc) return rc;
-    encode_tc_kernel<false><<<grid, kThreads, smem, s>>>(map->d, src, (const uint8_t*)enc->w16, (int)enc->w16_bytes,
-                                                          n_threads, (long long*)map->stats, dbg);
-  }
-  BNV_LAUNCH_CHECK("encode_tc_kernel");
+int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s) {
+  // the record count lives on the device (ctr[4]); the grid is sized for the most the prepass can have written
+  const size_t smem = smem_bytes(enc->in_pad);
+  int rc = set_smem(encode_chain_kernel, smem);
+  if (rc) return rc;
+  const int grid = grid_for(((max_records + 127) / 128) * 8);        // units = (tile, corner)
+  encode_chain_kernel<<<grid, kThreads, smem, s>>>(map->d, (const uint8_t*)enc->w16, (int)enc->w16_bytes);
+  BNV_LAUNCH_CHECK("encode_chain_kernel");
   return BNV_OK;
 }
 

@@ -245,10 +245,13 @@ int bnv_tsdf_copy(bnv_tsdf_t* tsdf, int which, float* out_dev, void* stream);
 int bnv_tsdf_prior(bnv_tsdf_t* tsdf, double truncated_dist, double sdf_delta_weight, float* out_dev, void* stream);
 
 /* Per-kernel device timing for bench.py's roofline: when enabled, bnv_fuse_frame / bnv_fuse_points
- * record CUDA events on `stream` around the encode kernel and the finalize kernel.
+ * record CUDA events on `stream` around the encode kernels and the finalize kernel.
  * bnv_map_get_timing waits for the last recorded call (host sync) and returns both durations. */
 int bnv_map_set_timing(bnv_map_t* map, int enable);
 int bnv_map_get_timing(bnv_map_t* map, float* encode_ms_host, float* finalize_ms_host);
+/* Same, per kernel of the frame: ms3_host = {prepass (back-projection + claims + compaction), encoder MLP kernel,
+ * finalize}; encode_ms above is the sum of the first two. */
+int bnv_map_get_timing_stages(bnv_map_t* map, float* ms3_host);
 
 /* Number of kernels this library launched since load (bench.py's gpu_launches evidence). */
 int64_t bnv_launch_count(void);

@@ -126,3 +126,83 @@ def test_tc_full_frame_paths_agree(model, dev):
     ref = vol.decode_voxel_blocks(model.nerf)
     config.set_mlp_mode("tc16")
     assert float((tc - ref).abs().max()) <= SDF_ATOL
+
+
+def test_tc_lounge_crop_512_grid(model, golden_dir, dev):
+    """The 512^3 lounge-crop goldens (minted from the unmodified reference sources) in the BENCHMARKED mode: voxel ids
+    exact, weights exact, features within fp16 operand noise, SDF <= 1e-4."""
+    g = np.load(os.path.join(golden_dir, "golden_lounge_crop.npz"))
+    spec = synth.stream_spec("lounge")
+    vol = _volume(spec, dev, pool_capacity=1 << 18)
+    for fi in range(2):
+        model.fuse_depth_frame(vol, _depth_to_dev(g["depth"][fi], dev), g["K"][fi], g["T_wc"][fi], spec.max_depth)
+    vol.check_status()
+    flat, feats, w, h = _map_sorted(vol)
+    rflat, rfeats, rw, rh = _golden_map_sorted(g, "recip", vol._n_xyz_host)
+    assert np.array_equal(flat, rflat)
+    np.testing.assert_allclose(w, rw, atol=1e-6, rtol=0)
+    _close_fp16(feats, rfeats)
+    vol.to_tensor()
+    vol.weights *= float(g["recip/weight_scale"])
+    prior = torch.from_numpy(g["recip/tsdf_delta"]).to(dev)[None, None]
+    for qk, sk, p in (("q_mesh", "sdf_mesh", None), ("q_mesh", "sdf_mesh_prior", prior), ("q_rand", "sdf_rand_prior", prior)):
+        q = torch.from_numpy(g["recip/" + qk].reshape(-1, 3)).to(dev)[None, :, None, :]
+        sdf = vol.decode_pts(q, model.nerf, p, is_coords=True)[0, :, 0, 0].cpu().numpy()
+        assert np.abs(sdf - g["recip/" + sk].reshape(-1)).max() <= SDF_ATOL
+
+
+def test_tc_lounge_full_frame_vs_oracle(model, tcnn_params, dev):
+    """BASELINE.json configs[1] at full size in the benchmarked mode, DIRECTLY against the oracle: two 640x480 lounge
+    frames fused into the 512^3 grid by the tensor-core path vs oracle.encode_pointcloud / integrate on the same frames
+    (local_point_fusion.py:81-151,647-673): voxel ids, counts and weights exact, features within fp16 operand noise,
+    27-sample SDF of 3000 voxels <= 1e-4."""
+    spec = synth.stream_spec("lounge")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vol = _volume(spec, dev, pool_capacity=1 << 21)
+    assert vol._n_xyz_host == (512, 512, 512)
+    vm = O.VoxelMap(grid)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    for fi in range(2):
+        d, K, T = synth.make_frame(spec, fi, seed=2)
+        assert d.shape == (480, 640)
+        model.fuse_depth_frame(vol, _depth_to_dev(d, dev), K, T, spec.max_depth, stats=stats)
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        pts6 = O.backproject(depth, mask, K, T)
+        feats, counts, flat, coords, _, _ = O.encode_pointcloud(pts6, grid, tcnn_params["encoder"], 8)
+        O.integrate(vm, flat, feats, counts)
+        st = stats.tolist()
+        assert st[0] == int(mask.sum()) and st[3] == len(flat)          # valid pixels, voxels with count >= 8
+    vol.check_status()
+    flat, feats, w, h = _map_sorted(vol)
+    rflat = np.sort(np.fromiter(vm.index.keys(), dtype=np.int64))
+    assert len(flat) > 50_000 and np.array_equal(flat, rflat)
+    rfeats, rw, _, _ = vm.query(flat)
+    assert np.array_equal(w, rw.astype(np.float32))                     # clip(count / 32, 1) sums: exact counts
+    _close_fp16(feats, rfeats)
+    coords = vol.to_tensor()[0]
+    vol.weights += 8.0
+    vm.weights[: len(vm)] += 8.0
+    sel = np.linspace(0, len(flat) - 1, 3000).astype(np.int64)
+    q = O.meshlize_samples(coords[torch.from_numpy(sel).to(dev)].cpu().numpy())
+    sdf = vol.decode_pts(torch.from_numpy(q).to(dev)[None], model.nerf, None, is_coords=True)[0, :, :, 0].cpu().numpy()
+    ref = O.decode_pts(vm, q.reshape(-1, 3), tcnn_params["decoder"], 8).reshape(-1, 27)
+    assert np.abs(sdf - ref).max() <= SDF_ATOL, np.abs(sdf - ref).max()
+    assert (ref != np.float32(spec.voxel_size)).mean() > 0.3
+
+
+def test_host_buffer_call_with_stale_prefetch_hint(model, dev):
+    """A prefetch hint that is NOT followed (frame X hinted, frame Y passed): the call must wait for the hinted copy
+    before overwriting the staging buffer and fuse frame Y (advisor finding, round 1)."""
+    spec = synth.stream_spec("parity64")
+    va, vb = _volume(spec, dev, pool_capacity=1 << 16), _volume(spec, dev, pool_capacity=1 << 16)
+    fr = [synth.make_frame(spec, fi, seed=4) for fi in range(4)]
+    hosts = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in fr]
+    order = [0, 2, 1, 3]
+    for j, fi in enumerate(order):
+        d, K, T = fr[fi]
+        model.fuse_depth_frame(va, _depth_to_dev(d, dev), K, T, spec.max_depth)
+        wrong = hosts[(fi + 1) % 4]                     # never the frame the next call passes (order is 0,2,1,3)
+        model.fuse_depth_frame_host(vb, hosts[fi], K, T, spec.max_depth, next_depth_mm_host=wrong)
+    torch.cuda.synchronize()
+    for x, y in zip(_map_sorted(va), _map_sorted(vb)):
+        assert np.array_equal(x, y) or np.allclose(x, y, atol=2e-5, rtol=0)
