@@ -113,44 +113,88 @@ def oracle_frame(O, grid, vm, enc, d, K, T, max_depth, rows=None):
     return 0 if flat is None else len(flat)
 
 
-def cpu_port(spec, frames, n_steps, sample_rows):
-    """The oracle port of the hot path on the host cores; value scaled to whole frames/s."""
+def cpu_port(spec, frames, n_steps, warm=True, rows=None):
+    """The oracle port of the hot path on the host cores, WHOLE 640x480 frames (numpy; its matmuls use the BLAS
+    threads of the box).  Returns (frames/s, seconds per frame)."""
     from oracle import bnv_oracle as O
     p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
     grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
     vm = O.VoxelMap(grid)
     d, K, T = frames[0]
-    oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=8)       # warm BLAS
+    if warm:
+        oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=8)       # warm BLAS
     t0 = time.perf_counter()
     for i in range(n_steps):
         d, K, T = frames[i % len(frames)]
-        oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=sample_rows)
+        oracle_frame(O, grid, vm, p["encoder"], d, K, T, spec.max_depth, rows=rows)
     dt = (time.perf_counter() - t0) / n_steps
-    scale = spec.height / sample_rows
-    return 1.0 / (dt * scale), dt
+    return 1.0 / dt, dt
+
+
+def ref_tsdf(spec, frames, n_timed=5, voxel=0.025):
+    """The CPU path BASELINE.json names, as is: the reference's third_parties/fusion.py (numba parallel=True,
+    fusion.py:169-206,251-294) staged unmodified into oracle/_ref by build(); TSDFVolume(use_gpu=False).integrate at
+    the reference's fixed 2.5 cm (run_e2e.py:62) over the workload's volume; 1 warm-up call (JIT), median of n_timed.
+    Falls back to the numpy port (oracle/tsdf_oracle.py) when the staged file is absent."""
+    from oracle import bnv_oracle as O
+    from oracle import stage_ref
+    mn, mx, _ = O.get_world_range(spec.dimensions, voxel)
+    bnds = np.stack([mn, mx], 1).astype(np.float64)
+    deps = [O.load_depth_u16(frames[i % len(frames)][0], spec.max_depth)[0].astype(np.float32) for i in range(n_timed + 1)]
+    rgb = np.zeros(deps[0].shape + (3,), np.float32)
+    if stage_ref.available():
+        import contextlib, io
+        import numba
+        fusion = stage_ref.load_fusion()
+        with contextlib.redirect_stdout(io.StringIO()):
+            tv = fusion.TSDFVolume(bnds.copy(), voxel_size=voxel, use_gpu=False)
+        kind, threads = "reference", int(numba.get_num_threads())
+        dims = [int(v) for v in tv._vol_dim]
+    else:
+        from oracle.tsdf_oracle import TSDFOracle
+        tv = TSDFOracle(bnds, voxel)
+        kind, threads, n_timed = "port", 1, 1
+        dims = [int(v) for v in tv.dim]
+    ts = []
+    for i in range(n_timed + 1):
+        _, K, T = frames[i % len(frames)]
+        t0 = time.perf_counter()
+        tv.integrate(rgb, deps[i], K, T, 1.0)
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.median(ts[1:])) if len(ts) > 1 else ts[0]
+    return {"value": 1.0 / sec, "unit": "frames/s", "kind": kind, "threads": threads, "sec_per_frame": sec,
+            "warmup_sec": ts[0], "timed_calls": len(ts) - 1,
+            "sample": "third_parties/fusion.py TSDFVolume(use_gpu=False).integrate, %dx%dx%d voxels @ %g cm, 640x480 frames, "
+                      "1 warm-up + median of %d" % (dims[0], dims[1], dims[2], voxel * 100, len(ts) - 1)}
 
 
 def run_reference(args):
+    """--impl reference: the path's CPU implementation on the box's host cores, WHOLE frames, `steps` of them: the
+    numpy oracle port of the neural local fusion (the reference's own modules need tinycudann / Open3D / torch_scatter,
+    absent from this image), plus the reference's own coarse-TSDF CPU code for the reference's 'local' timer scope."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     spec, frames = make_frames(4)
-    sample_rows = 60
     steps = max(1, args.steps)
-    for _ in range(min(args.warmup, 1)):
-        cpu_port(spec, frames, 1, sample_rows)
-    fps, dt = cpu_port(spec, frames, steps, sample_rows)
+    rows = args.ref_rows or None          # tests only: crop the frames (the driver's runs use whole frames)
+    cpu_port(spec, frames, min(args.warmup, 1), warm=True, rows=rows)
+    fps, dt = cpu_port(spec, frames, steps, warm=False, rows=rows)
     cores = os.cpu_count()
-    sample = f"{sample_rows} of {spec.height} image rows per step (x{spec.height // sample_rows} scaled), numpy oracle port, BLAS threads <= {cores}"
+    tsdf = ref_tsdf(spec, frames, n_timed=1 if rows else 5, voxel=0.1 if rows else 0.025)
+    what = "whole 640x480 frames" if not rows else f"frames CROPPED to {rows} rows (--ref-rows, contract test only)"
+    sample = f"{steps} {what}, numpy oracle port (oracle/bnv_oracle.py, float64 MLP), BLAS threads <= {cores}"
     print(json.dumps({
         "impl": "reference", "metric": "fusion_frames_per_sec", "value": fps, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * (spec.height / sample_rows),
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC, "frames": 4, "mlp": "float64 numpy (oracle port)"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample, "tsdf": tsdf},
+        "local_scope": {"value": 1.0 / (dt + tsdf["sec_per_frame"]), "unit": "frames/s",
+                        "what": "neural fusion (port) + coarse TSDF (%s) per frame, reference 'local' timer scope "
+                                "(run_e2e.py:78-109)" % tsdf["kind"]},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
-
 
 
 def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick_log2, exchange, n_frames=8):
@@ -422,20 +466,10 @@ def run_b200(args):
     scatter_bytes = 2 * H * W + 64 + touched_total / args.steps * 44 + kept_total / args.steps * 80
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        fps, dt = cpu_port(spec, frames, 2, 60)
-        # the CPU path BASELINE.json names: third_parties/fusion.py TSDFVolume CPU mode (oracle port), 206^3 @ 2.5 cm
-        from oracle.tsdf_oracle import TSDFOracle
-        from oracle import bnv_oracle as O
-        tv = TSDFOracle(np.stack([mn, mx], 1), 0.025)
-        d0, K0, T0 = frames[0]
-        dep = O.load_depth_u16(d0, spec.max_depth)[0].astype(np.float32)
-        t0 = time.perf_counter()
-        tv.integrate(np.zeros(d0.shape + (3,), np.float32), dep, K0, T0, 1.0)
-        t_tsdf = time.perf_counter() - t0
+        fps, dt = cpu_port(spec, frames, 2)
         cpu = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "2 steps of 60/480 image rows (x8 scaled) through oracle/bnv_oracle.py (numpy, float64 MLP)",
-               "tsdf_cpu_frames_per_sec": 1.0 / t_tsdf,
-               "tsdf_sample": "1 frame, third_parties/fusion.py CPU-mode port (oracle/tsdf_oracle.py), %dx%dx%d voxels @ 2.5 cm" % tuple(tsdf_dims)}
+               "sample": "2 whole 640x480 frames through oracle/bnv_oracle.py (numpy, float64 MLP, BLAS threads)",
+               "tsdf": ref_tsdf(spec, frames)}
     if rank == 0:
         out = {
             "metric": "fusion_frames_per_sec", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world,
@@ -602,6 +636,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,
                     help="opt-in: BASELINE configs[4] paced ARKit-shape stream (e.g. 60), prints latency percentiles instead")

@@ -74,6 +74,8 @@ SIGNATURES = {
     "bnv_fuse_points": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_decode_sdf": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "bnv_decode_sdf_backward": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _I64, _P, C.c_int, _P, _P, _P]),
+    "bnv_mesh_count": (C.c_int, [_P, _I64, _P, _P]),
+    "bnv_mesh_emit": (C.c_int, [_P, _P, _I64, _P, C.c_double, _P, _P, _I64, _P, _P, _P, _P]),
     "bnv_decode_voxel_blocks": (C.c_int, [_P, _I64, _I64, _P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
 }
 

@@ -349,13 +349,23 @@ int bnv_map_reset(bnv_map_t* m, void* stream) {
   return BNV_OK;
 }
 
+// latched device-side faults -> error code + message
+static int status_rc(const bnv_map_t* m, int32_t bits) {
+  if (bits & kErrCapacity) { set_error("voxel map capacity exceeded (pool capacity %d voxels, halo capacity %d records): voxels were dropped", m->d.cap, m->d.halo_cap); return BNV_E_CAPACITY; }
+  if (bits & kErrRange) { set_error("voxel key outside the %d x %d x %d grid", m->d.g.n[0], m->d.g.n[1], m->d.g.n[2]); return BNV_E_RANGE; }
+  if (bits & kErrExchange) { set_error("peer-memory halo exchange timed out waiting for another rank"); return BNV_E_CUDA; }
+  return BNV_OK;
+}
+
 int bnv_map_size(bnv_map_t* m, int64_t* n_active_host, void* stream) {
   if (!m || !n_active_host) { set_error("bnv_map_size: null argument"); return BNV_E_ARG; }
   int32_t c[4];
   BNV_CUDA(cudaMemcpyAsync(c, m->d.ctr, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   BNV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   *n_active_host = c[0] < m->d.cap ? c[0] : m->d.cap;
-  return BNV_OK;
+  // every host-side reader of the map (len / to_tensor / save / load) comes through here: a latched fault means
+  // voxels were dropped, so the size call fails loudly instead of handing out a truncated map
+  return status_rc(m, c[2]);
 }
 
 int bnv_map_status(bnv_map_t* m, void* stream) {
@@ -363,10 +373,7 @@ int bnv_map_status(bnv_map_t* m, void* stream) {
   int32_t c[4];
   BNV_CUDA(cudaMemcpyAsync(c, m->d.ctr, sizeof(c), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   BNV_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  if (c[2] & kErrCapacity) { set_error("voxel map capacity exceeded (capacity %d, frame rows %d)", m->d.cap, m->d.fcap); return BNV_E_CAPACITY; }
-  if (c[2] & kErrRange) { set_error("voxel key outside the %d x %d x %d grid", m->d.g.n[0], m->d.g.n[1], m->d.g.n[2]); return BNV_E_RANGE; }
-  if (c[2] & kErrExchange) { set_error("peer-memory halo exchange timed out waiting for another rank"); return BNV_E_CUDA; }
-  return BNV_OK;
+  return status_rc(m, c[2]);
 }
 
 int bnv_map_set_shard(bnv_map_t* m, int rank, int world, int brick_log2) {

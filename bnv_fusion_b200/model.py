@@ -203,7 +203,7 @@ class LitFusionPointNet(nn.Module):
 
     # ---- encode ------------------------------------------------------------------------------------
     def _volume_for(self, n_xyz, bound_min, voxel_size):
-        key = geometry_key(n_xyz, bound_min, voxel_size)
+        key = geometry_key(n_xyz, bound_min, voxel_size) + (self.device.index or 0,)
         vol = _REGISTRY.get(key)
         if vol is None:
             vol = self._scratch.get(key)
@@ -213,7 +213,7 @@ class LitFusionPointNet(nn.Module):
             dims = (np.asarray(n, np.float64) - 2) * float(voxel_size)
             vol = SparseVolume(self.feat_dims, float(voxel_size), dims, self.min_pts_in_grid,
                                device=str(self.device), pool_capacity=1024)
-            if geometry_key(vol._n_xyz_host, vol.min_coords, voxel_size) != key:
+            if geometry_key(vol._n_xyz_host, vol.min_coords, voxel_size) + (vol._dev_index,) != key:
                 raise RuntimeError("encode_pointcloud: no SparseVolume matches the given grid geometry")
             self._scratch[key] = vol
         return vol

@@ -17,7 +17,11 @@ import torch
 from . import _lib
 from . import config
 
-_REGISTRY = {}   # geometry key -> SparseVolume (lets encode_pointcloud find the map's scratch)
+import weakref
+
+# geometry key (+ device) -> SparseVolume: lets encode_pointcloud find the map that owns the per-frame scratch.
+# Weak references: `del vol` frees the volume's HBM; the latest volume of a geometry on a device wins.
+_REGISTRY = weakref.WeakValueDictionary()
 
 
 def get_world_range(dimensions, voxel_size):
@@ -65,6 +69,28 @@ class _DecodeFn(torch.autograd.Function):
         return grad, None, None, None, None, None, None, None
 
 
+class TriangleMesh:
+    """Minimal stand-in for trimesh.Trimesh (absent from this image): what NeuralMap / run_e2e.py touch on the
+    meshlize result -- `.vertices`, `.faces`, `.export(path)` (binary little-endian PLY)."""
+
+    def __init__(self, vertices, faces):
+        self.vertices = np.asarray(vertices, np.float32)
+        self.faces = np.asarray(faces, np.int64)
+
+    def export(self, path):
+        v, f = self.vertices, self.faces.astype(np.int32)
+        with open(path, "wb") as fh:
+            fh.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+                      "property float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n"
+                      % (len(v), len(f))).encode())
+            fh.write(v.astype("<f4").tobytes())
+            rec = np.empty(len(f), dtype=[("n", "u1"), ("i", "<i4", (3,))])
+            rec["n"] = 3
+            rec["i"] = f
+            fh.write(rec.tobytes())
+        return path
+
+
 class SparseVolume:
     def __init__(self, n_feats, voxel_size, dimensions, min_pts_in_grid, capacity=100000,
                  device="cuda:0", max_points=None, pool_capacity=None):
@@ -98,7 +124,7 @@ class SparseVolume:
                                                 self._pool, self._max_points, self._dev_index),
                        "bnv_map_create")
         self.reset(capacity, _fresh=True)
-        _REGISTRY[geometry_key(n_xyz, bmin32, voxel_size)] = self
+        _REGISTRY[geometry_key(n_xyz, bmin32, voxel_size) + (self._dev_index,)] = self
 
         self.avg_n_pts = 0
         self.n_pts_list = []
@@ -111,9 +137,6 @@ class SparseVolume:
             h, self._handle = self._handle, None
             if h:
                 self._lib.bnv_map_destroy(h)
-            for k, v in list(_REGISTRY.items()):
-                if v is self:
-                    del _REGISTRY[k]
         except Exception:
             pass
 
@@ -140,6 +163,7 @@ class SparseVolume:
     def reset(self, capacity=None, _fresh=False):
         """sparse_volume.py:587-600."""
         if not _fresh:
+            self._join_halo()
             _lib.check(self._lib.bnv_map_reset(self._handle, self._stream()), "bnv_map_reset")
         self.features = None
         self.weights = None
@@ -186,6 +210,7 @@ class SparseVolume:
         """upsert (sparse_volume.py:561-585)."""
         if len(keys) == 0:
             return None
+        self._join_halo()
         keys = keys.reshape(-1, 3).long().contiguous()
         n = keys.shape[0]
         f = new_feats.detach().reshape(n, self.n_feats).float().contiguous()
@@ -201,6 +226,7 @@ class SparseVolume:
         assert shapes[-1] == 3
         if n_pts == 0:
             return None, None, None
+        self._join_halo()
         k = keys.reshape(-1, 3).long().contiguous()
         out_feats = torch.empty((n_pts, self.n_feats), device=self.device)
         out_weights = torch.empty((n_pts, 1), device=self.device)
@@ -321,35 +347,51 @@ class SparseVolume:
                                                      self._stream()), "bnv_decode_voxel_blocks")
         return out
 
+    def extract_triangles(self, sdf_blocks, weld=True):
+        """Marching cubes over the sampled blocks of the active voxels, on the device (sparse_volume.py:738-766).
+
+        sdf_blocks [A,3,3,3] from decode_voxel_blocks.  Returns (vertices [V,3] float32, faces [T,3] int64) CUDA tensors
+        in world units; weld=True merges the vertices neighbouring blocks share (exact: by lattice-edge id),
+        weld=False keeps the reference's per-block triangle soup (3 vertices per triangle)."""
+        assert self.active_coordinates is not None, "call self.to_tensor() first."
+        n = self.active_coordinates.shape[0]
+        sdf = sdf_blocks.detach().reshape(n, 27).float().contiguous()
+        coords = self.active_coordinates.contiguous()
+        offsets = torch.empty(n + 1, dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.bnv_mesh_count(_lib.ptr(sdf), n, _lib.ptr(offsets), self._stream()), "bnv_mesh_count")
+        n_tri = int(offsets[-1].item())             # host sync (the reference syncs once per 500 voxels)
+        verts = torch.empty((3 * n_tri, 3), dtype=torch.float32, device=self.device)
+        keys = torch.empty(3 * n_tri, dtype=torch.int64, device=self.device)
+        mn = np.ascontiguousarray(self.min_coords.detach().cpu().numpy().astype(np.float32))
+        nxyz = (C.c_int32 * 3)(*self._n_xyz_host)
+        _lib.check(self._lib.bnv_mesh_emit(_lib.ptr(sdf), _lib.ptr(coords), n, _lib.ptr(offsets), float(self.voxel_size),
+                                           _lib.ptr(mn), nxyz, n_tri, _lib.ptr(verts), _lib.ptr(keys), None,
+                                           self._stream()), "bnv_mesh_emit")
+        if not weld or n_tri == 0:
+            return verts, torch.arange(3 * n_tri, device=self.device).reshape(-1, 3)
+        uk, inv = torch.unique(keys, return_inverse=True)
+        first = torch.full((uk.shape[0],), 3 * n_tri, dtype=torch.int64, device=self.device)
+        first.scatter_reduce_(0, inv, torch.arange(3 * n_tri, device=self.device), reduce="amin")
+        return verts[first], inv.reshape(-1, 3)
+
     def meshlize(self, nerf, sdf_delta=None, path=None):
         """create mesh from the implicit volume (sparse_volume.py:697-766).
 
-        The SDF sampling (the hot half) runs on the GPU in one launch for all active voxels; the
-        per-voxel marching cubes of the reference (skimage, CPU) is outside this round's scope
-        (SURVEY.md §8f rank 3): it is used when scikit-image and trimesh are installed, otherwise
-        the sampled blocks are returned."""
+        SDF sampling (one launch for all active voxels) and marching cubes (bnv_mesh_count / bnv_mesh_emit) both run
+        on the GPU; only the finished mesh is copied to the host.  Returns (active_pts, mesh) like the reference:
+        a trimesh.Trimesh when trimesh is installed, else a TriangleMesh (same .vertices / .faces / .export)."""
         assert self.active_coordinates is not None, "call self.to_tensor() first."
         sdf = self.decode_voxel_blocks(nerf, sdf_delta)
         active_pts = (self.active_coordinates * self.voxel_size + self.min_coords).detach().cpu().numpy()
+        verts, faces = self.extract_triangles(sdf, weld=False)    # the reference concatenates per-block meshes unwelded
+        if faces.shape[0] == 0:
+            return None                                           # sparse_volume.py:757-758
+        v, f = verts.cpu().numpy(), faces.cpu().numpy()
         try:
-            from skimage.measure import marching_cubes
             import trimesh
+            mesh = trimesh.Trimesh(vertices=v, faces=f, process=False)
         except ImportError:
-            return active_pts, sdf
-        sdf_np = sdf.cpu().numpy()
-        coords = self.active_coordinates.cpu().numpy()
-        all_v, all_f, last = [], [], 0
-        for j in range(sdf_np.shape[0]):
-            if sdf_np[j].max() > 0. and sdf_np[j].min() < 0.:
-                verts, faces, _, _ = marching_cubes(sdf_np[j], level=0., spacing=[0.5] * 3)
-                verts += coords[j] - 0.5
-                all_v.append(verts)
-                all_f.append(faces + last)
-                last += np.max(faces) + 1
-        if not all_v:
-            return None
-        v = np.concatenate(all_v, 0) * self.voxel_size + self.min_coords.cpu().numpy()
-        mesh = trimesh.Trimesh(vertices=v, faces=np.concatenate(all_f, 0), process=False)
+            mesh = TriangleMesh(v, f)
         if path is not None:
             mesh.export(path)
         return active_pts, mesh

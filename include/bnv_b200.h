@@ -83,7 +83,8 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
 int bnv_map_destroy(bnv_map_t* map);
 /* Drop all voxels (SparseVolume.reset, sparse_volume.py:587-600). */
 int bnv_map_reset(bnv_map_t* map, void* stream);
-/* Number of active voxels and latched device-side status.  Host sync on `stream`. */
+/* Number of active voxels and latched device-side status.  Host sync on `stream`.  bnv_map_size also fails (after
+ * writing the count) when a fault is latched: a map that dropped voxels is never read silently. */
 int bnv_map_size(bnv_map_t* map, int64_t* n_active_host, void* stream);
 int bnv_map_status(bnv_map_t* map, void* stream);
 /* Tile ownership for the multi-GPU shard: 3-D checkerboard of 2^brick_log2 bricks, a voxel belongs to
@@ -221,6 +222,21 @@ int bnv_decode_voxel_blocks(bnv_map_t* map, int64_t first, int64_t count, const 
                             const float* weights_rows_dev, int64_t n_rows, const bnv_mlp_t* dec,
                             int min_pts, int mode, const float* tsdf_delta_dev,
                             const int32_t* tsdf_dims_host, float* out_sdf_dev, void* stream);
+
+/* ---- mesh extraction ------------------------------------------------------
+ * The second half of SparseVolume.meshlize (src/models/sparse_volume.py:738-766): marching cubes at level 0 over the
+ * 3x3x3 sample block of every active voxel (sample spacing 0.5 voxel; a block is meshed iff max > 0 and min < 0, :740),
+ * vertices at (coord - 0.5 + 0.5 * index) * voxel_size + min_coords (:755,762), per-block meshes concatenated in voxel
+ * order (:758-761).  Replaces one skimage.measure.marching_cubes call per voxel on the CPU (with a D2H per 500 voxels).
+ * sdf_blocks_dev [n,27] is the output of bnv_decode_voxel_blocks; coords_dev [n,3] int64 the exported voxel coordinates.
+ *   bnv_mesh_count: tri_offsets_dev int32[n+1] <- exclusive scan of the triangles per voxel (offsets[n] = total).
+ *   bnv_mesh_emit : verts_dev float32 [3T,3] (triangle t = rows 3t..3t+2, outward = towards sdf > 0), keys_dev int64 [3T]
+ *                   (id of the half-voxel lattice edge the vertex lies on: equal ids <=> the same vertex, which is what
+ *                   welds the per-block meshes without a distance threshold), tri_voxel_dev int32 [T] nullable. */
+int bnv_mesh_count(const float* sdf_blocks_dev, int64_t n_voxels, int32_t* tri_offsets_dev, void* stream);
+int bnv_mesh_emit(const float* sdf_blocks_dev, const int64_t* coords_dev, int64_t n_voxels, const int32_t* tri_offsets_dev,
+                  double voxel_size, const float* min_coords_host, const int32_t* n_xyz_host, int64_t tri_capacity,
+                  float* verts_dev, int64_t* keys_dev, int32_t* tri_voxel_dev, void* stream);
 
 /* ---- coarse TSDF prior -------------------------------------------------
  * Replaces third_parties/fusion.py TSDFVolume (constructor :22-167, integrate :208-294 -- CPU mode

@@ -60,7 +60,7 @@ def test_bench_reference_arm_contract():
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-rows", "40"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]

@@ -277,6 +277,8 @@ def test_map_insert_query_roundtrip(dev):
     vol.insert(miss[2:3], feats[:1], w[:1], h[:1])
     with pytest.raises(RuntimeError):
         vol.check_status()
+    with pytest.raises(RuntimeError):       # every host-side reader fails loudly once a fault is latched
+        vol.to_tensor()
 
 
 def test_full_frame_paths_agree_and_properties(model, dev):
