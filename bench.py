@@ -205,7 +205,7 @@ def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick
     from bnv_fusion_b200.volume import SparseVolume
     from bnv_fusion_b200.dist import TileShardedFusion
     vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
-    sh = TileShardedFusion(vol, model, rank, world, brick_log2=brick_log2, exchange=exchange)
+    sh = TileShardedFusion(vol, model, rank, world, brick_log2=brick_log2, exchange=exchange, exchange_every=5)
     devf = [torch.from_numpy(frames[i][0].view(np.int16).copy()).to(dev).view(torch.uint16) for i in range(n_frames)]
     for i in range(n_frames):
         sh.fuse_depth_frame(devf[i], frames[i][1], frames[i][2], spec.max_depth)
@@ -289,7 +289,8 @@ def run_b200(args):
     shard = None
     if world > 1:
         from bnv_fusion_b200.dist import TileShardedFusion
-        shard = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange)
+        shard = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange,
+                                  exchange_every=args.exchange_every)
     H, W = spec.height, spec.width
     host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
     devf = [h.to(dev).view(torch.uint16) for h in host]
@@ -479,7 +480,8 @@ def run_b200(args):
             "config": {"workload": WORKLOAD_DESC, "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"tile shard over {world} GPUs, 3-D checkerboard of {1 << args.brick_log2}-voxel bricks, " +
-                       ("one all-gather per frame" if args.exchange == "nccl" else "peer-memory boundary routing")},
+                       (f"one all-gather of boundary voxels per {args.exchange_every} frames" if args.exchange == "nccl"
+                        else f"peer-memory boundary routing every {args.exchange_every} frames")},
             "value_warm": 1e3 / warm_ms,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
                     "d2h_bytes_per_step": 32,
@@ -579,7 +581,8 @@ def run_paced(args):
     target, pre = model, (vol,)
     if world > 1:
         from bnv_fusion_b200.dist import TileShardedFusion
-        target, pre = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange), ()
+        target, pre = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange,
+                                        exchange_every=args.exchange_every), ()
     host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
     stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
 
@@ -641,9 +644,11 @@ def main():
     ap.add_argument("--paced-fps", type=float, default=0.0,
                     help="opt-in: BASELINE configs[4] paced ARKit-shape stream (e.g. 60), prints latency percentiles instead")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
-                    help="tile shard boundary exchange: one NCCL all-gather per frame (default) or the experimental "
-                         "peer-memory routing (csrc/bnv_p2p.cu)")
-    ap.add_argument("--brick-log2", type=int, default=6, help="tile shard: owner bricks of 2^b voxels per side")
+                    help="tile shard boundary exchange: one NCCL all-gather per epoch (default) or sender-routed stores "
+                         "into the peers' inboxes over NVLink (csrc/bnv_p2p.cu)")
+    ap.add_argument("--brick-log2", type=int, default=5, help="tile shard: owner bricks of 2^b voxels per side")
+    ap.add_argument("--exchange-every", type=int, default=16,
+                    help="tile shard: frames per boundary-exchange epoch (halo copies are only read by decode; reads flush)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if os.environ.get("BNV_WATCHDOG"):         # diagnosing hangs: dump every thread's stack and exit

@@ -52,13 +52,12 @@ SIGNATURES = {
     "bnv_map_set_timing": (C.c_int, [_P, C.c_int]),
     "bnv_map_get_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bnv_map_get_timing_stages": (C.c_int, [_P, C.POINTER(C.c_float)]),
-    "bnv_map_set_halo_buffer": (C.c_int, [_P, _P, _I64]),
-    "bnv_map_halo_begin": (C.c_int, [_P, _P]),
+    "bnv_map_halo_enable": (C.c_int, [_P, _I64]),
+    "bnv_map_halo_pack": (C.c_int, [_P, _P, _I64, _P]),
     "bnv_map_insert_halo": (C.c_int, [_P, _P, C.c_int, _I64, _P]),
     "bnv_exchange_create": (C.c_int, [C.POINTER(_P), _P, _I64]),
     "bnv_exchange_handle": (C.c_int, [_P, _P]),
     "bnv_exchange_connect": (C.c_int, [_P, _P]),
-    "bnv_exchange_begin_frame": (C.c_int, [_P, _P]),
     "bnv_exchange_push": (C.c_int, [_P, _P]),
     "bnv_exchange_join": (C.c_int, [_P, _P]),
     "bnv_exchange_destroy": (C.c_int, [_P]),

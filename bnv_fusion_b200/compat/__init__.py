@@ -91,6 +91,21 @@ def install(reference_root: str | None = None):
     tp.fusion = tf
 
     vu = _voxel_utils_module()
+    if root:
+        # the reference's remaining helpers (get_frustrum_range, depth_to_tsdf, ...): executed from the reference file
+        # under a private name; the three hot-path functions above keep their B200 definitions
+        ref_file = os.path.join(root, "src", "utils", "voxel_utils.py")
+        if os.path.exists(ref_file):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_bnv_ref_voxel_utils", ref_file)
+            ref_vu = importlib.util.module_from_spec(spec)
+            try:
+                spec.loader.exec_module(ref_vu)
+                for k, v in vars(ref_vu).items():
+                    if not k.startswith("__") and not hasattr(vu, k):
+                        setattr(vu, k, v)
+            except ImportError:
+                pass                       # a dependency of the reference file is missing: hot-path functions only
     sys.modules[vu.__name__] = vu
     utils.voxel_utils = vu
     if root and root not in sys.path:

@@ -66,16 +66,21 @@ struct MapDev {
   // allocated by that first row from ctr[1].  Scratch rows are therefore contiguous in first-touch order
   // (fkeys / fsum rows [0, n_touched)), finalize streams them and zeroes the table entries it visits.
   unsigned long long* ftable;  // [n_vox]
+  unsigned long long* ftable_dummy;   // [1024] sink of the prepass' no-op atomics (lanes without a run to count)
   int32_t* fkeys;       // [fcap] flat id of scratch row
   long long* fsum;      // [fcap, 8] 2^30 fixed-point int64 sums (exact-parity mode: order-independent => deterministic);
                         // the tensor-core mode uses the same buffer as float [fcap, 8]
   float* prec;          // [max_points, 8] compacted in-bounds point records of the frame: voxel-space xyz, normal, pad
   int32_t fcap;         // min(8 * max_points, n_vox)
-  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter, [4] n point records
+  // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter, [4] n point records,
+  // [5] n dirty shell voxels
   int32_t* ctr;
-  // halo buffer of the tile shard (nullable): [int32 count, pad[9], records of 10 x 4 B]
-  int32_t* halo;
-  int32_t halo_cap;
+  // tile shard (nullable): voxels on the shell of their brick that were integrated since the last boundary exchange
+  // are remembered once each (flag per pool slot + list of slots, counter ctr[5]); bnv_map_halo_pack turns the list
+  // into records [int32 count, pad[9], records of 10 x 4 B] with the voxels' CURRENT values
+  int32_t* dirty_flag;  // [cap]
+  int32_t* dirty_list;  // [dirty_cap]
+  int32_t dirty_cap;
 };
 
 __host__ __device__ inline int owner_of(const GeomDev& g, int x, int y, int z) {

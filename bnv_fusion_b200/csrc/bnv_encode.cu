@@ -65,9 +65,42 @@ __global__ void compact_pts_kernel(const float* __restrict__ pts, const int32_t*
 // ------------------------------------------------------------------------------------------- //
 constexpr int kPreThreads = kTileW * kTileH;   // 256: one 32 x 8 pixel tile (a warp = 32 pixels of one image row)
 
+// NP x 32 (key, run length) pairs of a warp: NP independent, unconditional 32-bit atomics per lane on the LOW word
+// of the table entries (the count) -- straight-line code, so that all NP round trips to L2 are in flight before the
+// first result is read.  Returns the mask of pairs whose voxel this lane touched first (count was 0).
+template <int NP>
+__device__ __forceinline__ uint32_t claim_runs(const MapDev& m, const int2* __restrict__ runs, int n_runs, int lane,
+                                               unsigned int* dummy, int2 (&pr)[8]) {
+  unsigned int old[NP];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = j * 32 + lane;
+    pr[j] = (j < NP && i < n_runs) ? runs[i] : make_int2(-1, 0);
+  }
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    unsigned int* addr = pr[j].x >= 0 ? reinterpret_cast<unsigned int*>(m.ftable + pr[j].x) : dummy;
+    old[j] = atomicAdd(addr, (unsigned int)pr[j].y);
+  }
+  uint32_t win = 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j)
+    if (pr[j].x >= 0 && old[j] == 0u) win |= 1u << j;
+  return win;
+}
+
+__device__ __forceinline__ uint32_t claim_none(int2 (&pr)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pr[j] = make_int2(-1, 0);
+  return 0;
+}
+
 template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
+  // dbg (tools/prepass_ablation.py only; 0 in production): 1 no claim atomics, 2 no global counter atomics,
+  // 4 no back-projection (every pixel invalid), 8 no record / key stores
   __shared__ FrameTile tile;
+  __shared__ int2 s_runs[kPreThreads / 32][256];       // per warp: (voxel key, run length) of up to 8 x 32 runs
   __shared__ int s_new[kPreThreads / 32], s_keep[kPreThreads / 32], s_stat[3], s_base[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const GeomDev& g = m.g;
@@ -82,7 +115,7 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     __syncthreads();
     const int u = u0 + lane, v = v0 + warp;
     pix = v * src.cam.W + u;
-    if (u < src.cam.W && v < src.cam.H) valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
+    if (u < src.cam.W && v < src.cam.H && !(dbg & 4)) valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
   } else {
     const int64_t idx = (int64_t)blockIdx.x * kPreThreads + tid;
     pix = (int32_t)idx;
@@ -104,34 +137,45 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     fl[a] = floorf(c[a]);
     ce[a] = ceilf(c[a]);
   }
-  // ---- one 64-bit atomicAdd per run of lanes whose corner k is the same owned voxel ------------------------
-  unsigned long long old[8];
-  int32_t key[8];
-  uint32_t own = 0, issued = 0;
+  // ---- runs of lanes whose corner k is the same owned voxel -> (key, run length) pairs, compacted per warp ----
+  // Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE 64-bit atomicAdd of its length.
+  // The pairs are compacted into a per-warp shared-memory list first, so that the atomics are issued by dense,
+  // unconditional, independent instructions (lane j takes pairs j, j + 32, ...): all of a lane's round trips to L2
+  // are in flight together.  (Issued in place under `if (head)`, the compiler sinks each result test into its branch:
+  // eight serialised L2 round trips per thread, 55 % of this kernel's stall samples in profiles/r2a.)
+  uint32_t own = 0;
+  const bool sharded = g.world > 1;                                      // block-uniform
+  int n_runs = 0;                                                        // warp-uniform
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float nb[3];
     corner_of(k, fl, ce, nb);                                            // rule A3 (modules.py:178-247)
     const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-    const bool o = inb && owns(g, ix, iy, iz);
-    key[k] = o ? ix * g.nyz + iy * g.n[2] + iz : -1 - lane;              // rule A5 (int32); negatives never merge
+    bool o = inb;
+    if (sharded) o = o & (owner_of(g, ix, iy, iz) == g.rank);
+    const int32_t key = o ? ix * g.nyz + iy * g.n[2] + iz : -1 - lane;   // rule A5 (int32); negatives never merge
     own |= (o ? 1u : 0u) << k;
-    const int32_t prev = __shfl_up_sync(0xffffffffu, key[k], 1);
-    const bool head = lane == 0 || prev != key[k];
+    const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    old[k] = 1;
+    const uint32_t real = __ballot_sync(0xffffffffu, head && o);
     if (head && o) {
       const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
       const int run = rest ? __ffs(rest) : 32 - lane;
-      old[k] = atomicAdd(&m.ftable[key[k]], (unsigned long long)run);
-      issued |= 1u << k;
+      s_runs[warp][n_runs + __popc(real & ((1u << lane) - 1u))] = make_int2(key, run);
     }
+    n_runs += __popc(real);
   }
+  __syncwarp();
+  // ---- claim + count: lane j takes pairs j, j + 32, ...; a lane without a pair adds 0 to a private dummy word ----
+  unsigned int* dummy = reinterpret_cast<unsigned int*>(m.ftable_dummy + ((blockIdx.x * kPreThreads + tid) & 1023));
+  int2 pr[8];
+  const int2* runs = s_runs[warp];
+  const uint32_t win = (dbg & 1)       ? claim_none(pr)
+                       : n_runs <= 64  ? claim_runs<2>(m, runs, n_runs, lane, dummy, pr)
+                       : n_runs <= 128 ? claim_runs<4>(m, runs, n_runs, lane, dummy, pr)
+                                       : claim_runs<8>(m, runs, n_runs, lane, dummy, pr);
   // ---- first touchers allocate dense scratch rows; in-bounds points get a record slot ---------------------
-  uint32_t win = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (((issued >> k) & 1u) && ft_count(old[k]) == 0) win |= 1u << k;
   const int n_new = __popc(win);
   int incl = n_new;
 #pragma unroll
@@ -157,12 +201,12 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     if (warp == 0) {
       int t = 0;
       for (int w = 0; w < kPreThreads / 32; ++w) t += s_new[w];
-      s_base[0] = t ? atomicAdd(&m.ctr[1], t) : 0;
+      s_base[0] = (t && !(dbg & 2)) ? atomicAdd(&m.ctr[1], t) : 0;
     } else if (warp == 1) {
       int t = 0;
       for (int w = 0; w < kPreThreads / 32; ++w) t += s_keep[w];
-      s_base[1] = t ? atomicAdd(&m.ctr[4], t) : 0;
-    } else {
+      s_base[1] = (t && !(dbg & 2)) ? atomicAdd(&m.ctr[4], t) : (dbg & 2) ? (int)blockIdx.x * kPreThreads : 0;
+    } else if (!(dbg & 2)) {
       if (s_stat[0]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)s_stat[0]);
       if (s_stat[1]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), (unsigned long long)s_stat[1]);
       if (s_stat[2]) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 4), (unsigned long long)s_stat[2]);
@@ -175,14 +219,14 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     rec += s_keep[w];
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if ((win >> k) & 1u) {
+  for (int j = 0; j < 8; ++j)
+    if ((win >> j) & 1u) {
       // publish the dense row in the entry's high word (visible to the kernels that follow) and its key
-      atomicAdd(&m.ftable[key[k]], (unsigned long long)(uint32_t)row << 32);
-      m.fkeys[row] = key[k];
+      reinterpret_cast<int32_t*>(m.ftable + pr[j].x)[1] = row;
+      m.fkeys[row] = pr[j].x;
       ++row;
     }
-  if (keep) {
+  if (keep && !(dbg & 8)) {
     float4* r4 = reinterpret_cast<float4*>(m.prec + (size_t)rec * 8);
     r4[0] = make_float4(c[0], c[1], c[2], p[3]);
     r4[1] = make_float4(p[4], p[5], __int_as_float((int)own), __int_as_float(pix));
@@ -251,74 +295,77 @@ __device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new
 }
 
 // 3. finalize of the fused path: for every voxel touched this frame (dense scratch rows [0, n_touched)) -> mean,
-// count filter, running average into the persistent map; clears the scratch.  8 lanes per voxel (one feature each).
+// count filter, running average into the persistent map; clears the scratch.  ONE THREAD PER VOXEL: the kernel is a
+// chain of dependent scattered reads (key -> table entries -> map slot -> old features), i.e. latency x concurrency
+// bound, so every thread keeps its own voxel's chain in flight (an 8-lanes-per-voxel layout had 8x fewer chains in
+// flight and ran 23 us on 1.3e5 voxels); the 32-byte scratch and feature rows move as two 16-byte accesses.
 __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, bool f32acc, long long* __restrict__ stats,
                                                              long long* __restrict__ user_stats,
                                                              float* __restrict__ user_navg) {
   const int n_touched = m.ctr[1];
-  const int lane8 = threadIdx.x & 7;
-  const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);   // the 8 lanes that share a voxel
   int integrated = 0;
-  for (int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; t < n_touched;
-       t += ((int64_t)gridDim.x * blockDim.x) >> 3) {
-    const int32_t row = (int32_t)t;
-    const int32_t key = m.fkeys[row];
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_touched; t += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t key = m.fkeys[t];
     const int32_t cnt = ft_count(m.ftable[key]);
-    const float mean = scratch_mean(m, row, lane8, cnt, f32acc);
-    scratch_clear(m, row, lane8, f32acc);
-    if (cnt >= min_pts) {                                         // local_point_fusion.py:143-147
-      int32_t slot = 0;
-      if (lane8 == 0) {
-        slot = m.table[key];
-        if (slot < 0) {
-          slot = atomicAdd(&m.ctr[0], 1);
-          if (slot < m.cap) {
-            m.table[key] = slot;
-            m.keys[slot] = key;
-            m.weights[slot] = 0.f;
-            m.hits[slot] = 0.f;
-          } else {
-            atomicOr(&m.ctr[2], kErrCapacity);
-            slot = -1;
-          }
-          slot = slot < 0 ? -1 : (slot | 0x40000000);           // bit 30: freshly allocated
-        }
-      }
-      slot = __shfl_sync(gmask, slot, (threadIdx.x & 31) & ~7);
-      if (slot >= 0) {
-        const bool fresh = slot & 0x40000000;
-        slot &= 0x3fffffff;
-        const float w_new = fminf(__fmul_rn((float)cnt, 0.03125f), 1.0f);   // clip(count/32, max=1)
-        const float w_old = fresh ? 0.f : m.weights[slot];
-        const float f_old = fresh ? 0.f : m.feats[(size_t)slot * kFeat + lane8];
-        const float w = __fadd_rn(w_old, w_new);
-        const float f_new = fuse_feat(f_old, w_old, mean, w_new, w);
-        m.feats[(size_t)slot * kFeat + lane8] = f_new;
-        __syncwarp(gmask);
-        if (lane8 == 0) {
-          m.weights[slot] = w;
-          ++integrated;
-        }
-        const int kx = key / m.g.nyz, kr = key - kx * m.g.nyz, ky = kr / m.g.n[2], kz = kr - ky * m.g.n[2];
-        if (m.halo && on_brick_shell(m.g, kx, ky, kz)) {            // another rank may need it as a corner
-          int pos = 0;
-          if (lane8 == 0) pos = atomicAdd(&m.halo[0], 1);
-          pos = __shfl_sync(gmask, pos, (threadIdx.x & 31) & ~7);
-          if (pos < m.halo_cap) {
-            int32_t* rec = m.halo + 10 + (size_t)pos * 10;
-            reinterpret_cast<float*>(rec)[2 + lane8] = f_new;
-            if (lane8 == 0) {
-              rec[0] = key;
-              reinterpret_cast<float*>(rec)[1] = w;
-            }
-          } else if (lane8 == 0) {
-            atomicOr(&m.ctr[2], kErrCapacity);
-          }
-        }
+    int32_t slot = m.table[key];                                  // independent of the count: both reads in flight
+    m.ftable[key] = 0ull;
+    float mean[kFeat];                                            // scatter_mean, local_point_fusion.py:125
+    if (f32acc) {                                                 // tensor-core mode: fp32 partial sums (add_row_f32)
+      float4* s4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.fsum) + (size_t)t * kFeat);
+      const float4 a = s4[0], b = s4[1];
+      s4[0] = s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float s[kFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < kFeat; ++j) mean[j] = (float)((double)s[j] / (double)cnt);
+    } else {
+      longlong2* s2 = reinterpret_cast<longlong2*>(m.fsum + (size_t)t * kFeat);
+#pragma unroll
+      for (int j = 0; j < kFeat / 2; ++j) {
+        const longlong2 v = s2[j];
+        s2[j] = make_longlong2(0, 0);
+        mean[2 * j] = (float)(((double)v.x / kFixScale) / (double)cnt);
+        mean[2 * j + 1] = (float)(((double)v.y / kFixScale) / (double)cnt);
       }
     }
-    __syncwarp(gmask);
-    if (lane8 == 0) m.ftable[key] = 0ull;
+    if (cnt < min_pts) continue;                                  // local_point_fusion.py:143-147
+    bool fresh = false;
+    if (slot < 0) {
+      slot = atomicAdd(&m.ctr[0], 1);
+      if (slot >= m.cap) {
+        atomicOr(&m.ctr[2], kErrCapacity);
+        continue;
+      }
+      fresh = true;
+      m.table[key] = slot;
+      m.keys[slot] = key;
+      m.hits[slot] = 0.f;
+    }
+    float4* f4 = reinterpret_cast<float4*>(m.feats + (size_t)slot * kFeat);
+    float w_old = 0.f;
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+    if (!fresh) {
+      w_old = m.weights[slot];
+      oa = f4[0];
+      ob = f4[1];
+    }
+    const float w_new = fminf(__fmul_rn((float)cnt, 0.03125f), 1.0f);   // clip(count/32, max=1)
+    const float w = __fadd_rn(w_old, w_new);
+    const float f_old[kFeat] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+    float f_new[kFeat];
+#pragma unroll
+    for (int j = 0; j < kFeat; ++j) f_new[j] = fuse_feat(f_old[j], w_old, mean[j], w_new, w);
+    f4[0] = make_float4(f_new[0], f_new[1], f_new[2], f_new[3]);
+    f4[1] = make_float4(f_new[4], f_new[5], f_new[6], f_new[7]);
+    m.weights[slot] = w;
+    ++integrated;
+    if (m.dirty_list) {                                           // tile shard: another rank may need it as a corner
+      const int kx = key / m.g.nyz, kr = key - kx * m.g.nyz, ky = kr / m.g.n[2], kz = kr - ky * m.g.n[2];
+      if (on_brick_shell(m.g, kx, ky, kz) && atomicExch(&m.dirty_flag[slot], 1) == 0) {
+        const int pos = atomicAdd(&m.ctr[5], 1);                  // once per voxel and exchange epoch
+        if (pos < m.dirty_cap) m.dirty_list[pos] = slot;
+        else atomicOr(&m.ctr[2], kErrCapacity);
+      }
+    }
   }
   // one statistics atomic per block (same-address atomics serialise in L2)
   __shared__ int s_integrated;
@@ -483,6 +530,7 @@ const float* bnv_internal_simt_weights(const bnv_mlp_t* mlp);
 int bnv_internal_encode_tc(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
 
 namespace bnv {
+static int g_prepass_debug = 0;      // profiling ablations only (bnv_debug_prepass, not part of the ABI header)
 // kernels 1 + 2 of the frame: prepass over `n_threads` pixels / points, then the encoder MLP over the records
 static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int64_t n_threads,
                          const bnv_mlp_t* enc, int mode, cudaStream_t s) {
@@ -495,10 +543,10 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
   if (n_threads == 0) return BNV_OK;
   if (from_depth) {
     const unsigned tiles = (unsigned)(((src.cam.W + kTileW - 1) / kTileW) * ((src.cam.H + kTileH - 1) / kTileH));
-    frame_prepass_kernel<true><<<tiles, kPreThreads, 0, s>>>(map->d, src, (long long*)map->stats);
+    frame_prepass_kernel<true><<<tiles, kPreThreads, 0, s>>>(map->d, src, (long long*)map->stats, g_prepass_debug);
   } else {
     frame_prepass_kernel<false><<<(unsigned)((n_threads + kPreThreads - 1) / kPreThreads), kPreThreads, 0, s>>>(
-        map->d, src, (long long*)map->stats);
+        map->d, src, (long long*)map->stats, g_prepass_debug);
   }
   BNV_LAUNCH_CHECK("frame_prepass_kernel");
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[3], s));
@@ -516,13 +564,16 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
 }
 
 static int launch_finalize(bnv_map_t* map, int min_pts, int mode, int64_t* frame_stats, float* navg, cudaStream_t s) {
-  finalize_fused_kernel<<<148 * 8, 256, 0, s>>>(map->d, min_pts, mode == BNV_MLP_TC16, (long long*)map->stats, (long long*)frame_stats, navg);
+  finalize_fused_kernel<<<148 * 4, 256, 0, s>>>(map->d, min_pts, mode == BNV_MLP_TC16, (long long*)map->stats, (long long*)frame_stats, navg);
   BNV_LAUNCH_CHECK("finalize_fused_kernel");
   return BNV_OK;
 }
 }  // namespace bnv
 
 extern "C" {
+
+// profiling tool hook (tools/prepass_ablation.py); deliberately not declared in include/bnv_b200.h
+int bnv_debug_prepass(int flags) { g_prepass_debug = flags; return BNV_OK; }
 
 int bnv_backproject(bnv_map_t* map, const uint16_t* depth, int H, int W, const float* K, const float* T,
                     double max_depth, float* pts6, int32_t* n_valid, void* stream) {

@@ -166,6 +166,32 @@ __global__ void zlut_kernel(double* __restrict__ z) {
   if (i < 65536) z[i] = __ddiv_rn((double)i, 1000.0);
 }
 
+// boundary exchange, sender side: one record {flat id, weight, feat[8]} with the CURRENT values of every shell voxel
+// integrated since the last exchange (the dirty list holds each such slot once), flags cleared on the way
+__global__ void __launch_bounds__(256) halo_pack_kernel(MapDev m, int32_t* __restrict__ buf, int cap) {
+  const int n = min(min(m.ctr[5], m.dirty_cap), cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int32_t slot = m.dirty_list[i];
+    m.dirty_flag[slot] = 0;
+    const float4* f4 = reinterpret_cast<const float4*>(m.feats + (size_t)slot * kFeat);
+    const float4 a = f4[0], b = f4[1];
+    int32_t* rec = buf + 10 + (size_t)i * 10;                   // 40-byte records: 8-byte aligned
+    reinterpret_cast<int2*>(rec)[0] = make_int2(m.keys[slot], __float_as_int(m.weights[slot]));
+    reinterpret_cast<float2*>(rec)[1] = make_float2(a.x, a.y);
+    reinterpret_cast<float2*>(rec)[2] = make_float2(a.z, a.w);
+    reinterpret_cast<float2*>(rec)[3] = make_float2(b.x, b.y);
+    reinterpret_cast<float2*>(rec)[4] = make_float2(b.z, b.w);
+  }
+}
+__global__ void halo_pack_reset_kernel(MapDev m, int32_t* __restrict__ buf, int cap) {
+  if (threadIdx.x == 0) {
+    const int n = m.ctr[5];
+    if (n > m.dirty_cap || n > cap) atomicOr(&m.ctr[2], kErrCapacity);    // records were dropped
+    buf[0] = min(min(n, m.dirty_cap), cap);
+    m.ctr[5] = 0;
+  }
+}
+
 // upsert the halo records of the other ranks that this rank needs: 8 lanes per record
 __global__ void insert_halo_kernel(MapDev m, const int32_t* __restrict__ gathered, int world, int64_t cap) {
   const int64_t stride_words = 10 + cap * 10;
@@ -211,16 +237,29 @@ using namespace bnv;
 
 extern "C" {
 
-int bnv_map_set_halo_buffer(bnv_map_t* m, void* buf, int64_t cap) {
-  if (!m || cap < 0 || cap > 0x7fffffff) { set_error("bnv_map_set_halo_buffer: bad argument"); return BNV_E_ARG; }
-  m->d.halo = (int32_t*)buf;
-  m->d.halo_cap = buf ? (int32_t)cap : 0;
+int bnv_map_halo_enable(bnv_map_t* m, int64_t capacity_records) {
+  if (!m || capacity_records < 0 || capacity_records > 0x7fffffff) { set_error("bnv_map_halo_enable: bad argument"); return BNV_E_ARG; }
+  BNV_CUDA(cudaSetDevice(m->device));
+  BNV_CUDA(cudaDeviceSynchronize());
+  if (m->d.dirty_flag) cudaFree(m->d.dirty_flag);
+  if (m->d.dirty_list) cudaFree(m->d.dirty_list);
+  m->d.dirty_flag = m->d.dirty_list = nullptr;
+  m->d.dirty_cap = 0;
+  if (capacity_records == 0) return BNV_OK;
+  BNV_CUDA(cudaMalloc((void**)&m->d.dirty_flag, (size_t)m->d.cap * 4));
+  BNV_CUDA(cudaMalloc((void**)&m->d.dirty_list, (size_t)capacity_records * 4));
+  BNV_CUDA(cudaMemset(m->d.dirty_flag, 0, (size_t)m->d.cap * 4));
+  BNV_CUDA(cudaMemset(m->d.ctr + 5, 0, 4));
+  m->d.dirty_cap = (int32_t)capacity_records;
   return BNV_OK;
 }
 
-int bnv_map_halo_begin(bnv_map_t* m, void* stream) {
-  if (!m || !m->d.halo) { set_error("bnv_map_halo_begin: no halo buffer attached"); return BNV_E_ARG; }
-  BNV_CUDA(cudaMemsetAsync(m->d.halo, 0, 40, (cudaStream_t)stream));
+int bnv_map_halo_pack(bnv_map_t* m, void* buf, int64_t capacity_records, void* stream) {
+  if (!m || !buf || capacity_records <= 0 || !m->d.dirty_list) { set_error("bnv_map_halo_pack: bad argument (bnv_map_halo_enable first)"); return BNV_E_ARG; }
+  halo_pack_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(m->d, (int32_t*)buf, (int)(capacity_records < 0x7fffffff ? capacity_records : 0x7fffffff));
+  BNV_LAUNCH_CHECK("halo_pack_kernel");
+  halo_pack_reset_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(m->d, (int32_t*)buf, (int)(capacity_records < 0x7fffffff ? capacity_records : 0x7fffffff));
+  BNV_LAUNCH_CHECK("halo_pack_reset_kernel");
   return BNV_OK;
 }
 
@@ -275,6 +314,7 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
   alloc((void**)&d.table, g.n_vox * 4);
   alloc((void**)&d.ftable, g.n_vox * 8);
+  alloc((void**)&d.ftable_dummy, 1024 * 8);
   alloc((void**)&d.keys, (size_t)d.cap * 4);
   alloc((void**)&d.feats, (size_t)d.cap * kFeat * 4);
   alloc((void**)&d.weights, (size_t)d.cap * 4);
@@ -324,7 +364,7 @@ int bnv_map_destroy(bnv_map_t* m) {
   if (!m) return BNV_OK;
   cudaSetDevice(m->device);
   MapDev& d = m->d;
-  void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.prec,
+  void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.prec, d.ftable_dummy, d.dirty_flag, d.dirty_list,
                   d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
                   m->sort_vals_out, m->flags, m->scan, m->zlut, m->depth_stage[0], m->depth_stage[1], m->user_stats, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
@@ -346,12 +386,13 @@ int bnv_map_reset(bnv_map_t* m, void* stream) {
   int rc = fill_i32(m->d.table, m->d.g.n_vox, kEmpty, s);
   if (rc != BNV_OK) return rc;
   BNV_CUDA(cudaMemsetAsync(m->d.ctr, 0, 64, s));
+  if (m->d.dirty_flag) BNV_CUDA(cudaMemsetAsync(m->d.dirty_flag, 0, (size_t)m->d.cap * 4, s));
   return BNV_OK;
 }
 
 // latched device-side faults -> error code + message
 static int status_rc(const bnv_map_t* m, int32_t bits) {
-  if (bits & kErrCapacity) { set_error("voxel map capacity exceeded (pool capacity %d voxels, halo capacity %d records): voxels were dropped", m->d.cap, m->d.halo_cap); return BNV_E_CAPACITY; }
+  if (bits & kErrCapacity) { set_error("voxel map capacity exceeded (pool capacity %d voxels, boundary-exchange capacity %d records): voxels were dropped", m->d.cap, m->d.dirty_cap); return BNV_E_CAPACITY; }
   if (bits & kErrRange) { set_error("voxel key outside the %d x %d x %d grid", m->d.g.n[0], m->d.g.n[1], m->d.g.n[2]); return BNV_E_RANGE; }
   if (bits & kErrExchange) { set_error("peer-memory halo exchange timed out waiting for another rank"); return BNV_E_CUDA; }
   return BNV_OK;

@@ -13,8 +13,8 @@
 // local record buffers and the peers' inboxes are double-buffered by frame parity; a sender reuses parity b for
 // frame s only after every peer acknowledged frame s - 2 (ack sequence numbers written back the same way).
 //
-// Status: compiles for sm_100a; written at the end of round 1 without GPU time left, NOT yet run on
-// hardware -- the NCCL path stays the tested default.
+// The exchange is per EPOCH, not per frame: finalize remembers every shell voxel it integrates once (dirty list,
+// bnv_map.cu), and an epoch (every K frames, or when the map is read) packs their current values and routes them.
 #include <new>
 
 #include "bnv_common.cuh"
@@ -63,12 +63,13 @@ __global__ void wait_flags_kernel(const uint32_t* __restrict__ flags, uint32_t w
 }
 
 // sender: route this frame's boundary records to the ranks that need them
-__global__ void __launch_bounds__(256) halo_push_kernel(MapDev m, PeerPtrs peers, int buf, uint32_t seq, int64_t cap,
+__global__ void __launch_bounds__(256) halo_push_kernel(MapDev m, const int32_t* __restrict__ packed /* bnv_map_halo_pack */,
+                                                        PeerPtrs peers, int buf, uint32_t seq, int64_t cap,
                                                         int32_t* __restrict__ sent /*[world]*/, int32_t* __restrict__ done) {
   const GeomDev& g = m.g;
-  const int n = min(m.halo[0], m.halo_cap);
+  const int n = packed[0];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t* rec = m.halo + 10 + i * kRecWords;
+    const int32_t* rec = packed + 10 + i * kRecWords;
     const int32_t flat = rec[0];
     const int x = flat / g.nyz, rr = flat - x * g.nyz, y = rr / g.n[2], z = rr - y * g.n[2];
     uint32_t need = 0;                        // ranks owning a brick in the voxel's 26-neighbourhood
@@ -183,7 +184,6 @@ struct bnv_exchange {
   cudaEvent_t fused, pushed[2], upserted;
   bool pushed_valid[2];
   bool any_upsert;
-  bool frame_open;
 };
 
 extern "C" {
@@ -243,42 +243,30 @@ int bnv_exchange_connect(bnv_exchange_t* ex, const void* handles /* [world][64],
   return BNV_OK;
 }
 
-/* Start a frame on `stream`: attach the boundary-record buffer of this frame's parity to the map (once the push
- * that last read it has finished) and reset its count.  Replaces bnv_map_set_halo_buffer + bnv_map_halo_begin. */
-int bnv_exchange_begin_frame(bnv_exchange_t* ex, void* stream) {
-  if (!ex || !ex->connected) { set_error("bnv_exchange_begin_frame: exchange is not connected"); return BNV_E_ARG; }
-  if (ex->frame_open) { set_error("bnv_exchange_begin_frame: the previous frame was not pushed"); return BNV_E_ARG; }
-  cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t seq = ++ex->seq;
-  const int buf = (int)(seq & 1u);
-  if (ex->pushed_valid[buf]) BNV_CUDA(cudaStreamWaitEvent(s, ex->pushed[buf], 0));     // frame seq - 2 has been routed
-  ex->map->d.halo = ex->halo[buf];
-  ex->map->d.halo_cap = (int32_t)ex->halo_cap;
-  BNV_CUDA(cudaMemsetAsync(ex->halo[buf], 0, 40, s));
-  ex->frame_open = true;
-  return BNV_OK;
-}
-
-/* After bnv_fuse_frame* on `stream`: everything else happens on the exchange's side stream, overlapped with the
- * next frame -- route this frame's boundary records to the peers that need them, wait for every peer's records of
- * the same frame, upsert them, acknowledge. */
+/* One exchange epoch.  On `stream`: pack the records of the shell voxels integrated since the last exchange
+ * (bnv_map_halo_pack) into this epoch's record buffer.  Everything else happens on the exchange's side stream,
+ * overlapped with the frames that follow -- route the records to the peers that need them, wait for every peer's
+ * records of the same epoch, upsert them, acknowledge.  Every rank must call it at the same points of the stream. */
+int bnv_map_halo_pack(bnv_map_t* m, void* buf, int64_t capacity_records, void* stream);
 int bnv_exchange_push(bnv_exchange_t* ex, void* stream) {
   if (!ex || !ex->connected) { set_error("bnv_exchange_push: exchange is not connected"); return BNV_E_ARG; }
-  if (!ex->frame_open) { set_error("bnv_exchange_push: call bnv_exchange_begin_frame first"); return BNV_E_ARG; }
   cudaStream_t s = (cudaStream_t)stream;
-  const uint32_t seq = ex->seq;
+  const uint32_t seq = ++ex->seq;
   const int buf = (int)(seq & 1u);
   const long long timeout = 4000000000ll;                       // ~2 s of SM clock
   uint32_t* flags_ready = reinterpret_cast<uint32_t*>(ex->block);
   uint32_t* flags_ack = flags_ready + kMaxPeers;
+  if (ex->pushed_valid[buf]) BNV_CUDA(cudaStreamWaitEvent(s, ex->pushed[buf], 0));     // epoch seq - 2 has been routed
+  int rc = bnv_map_halo_pack(ex->map, ex->halo[buf], ex->halo_cap, stream);
+  if (rc) return rc;
   BNV_CUDA(cudaEventRecord(ex->fused, s));
   BNV_CUDA(cudaStreamWaitEvent(ex->side, ex->fused, 0));
-  if (seq > 2) {                                                // the peers' inbox parity `buf` was last used by frame seq - 2
+  if (seq > 2) {                                                // the peers' inbox parity `buf` was last used by epoch seq - 2
     wait_flags_kernel<<<1, 32, 0, ex->side>>>(flags_ack, seq - 2, ex->world, ex->rank, timeout, &ex->map->d.ctr[2]);
     BNV_LAUNCH_CHECK("wait_flags_kernel");
   }
-  MapDev d = ex->map->d;                                         // carries this frame's halo pointer
-  halo_push_kernel<<<64, 256, 0, ex->side>>>(d, ex->peers, buf, seq, ex->cap, ex->scratch, ex->scratch + kMaxPeers);
+  MapDev d = ex->map->d;
+  halo_push_kernel<<<64, 256, 0, ex->side>>>(d, ex->halo[buf], ex->peers, buf, seq, ex->cap, ex->scratch, ex->scratch + kMaxPeers);
   BNV_LAUNCH_CHECK("halo_push_kernel");
   BNV_CUDA(cudaEventRecord(ex->pushed[buf], ex->side));
   ex->pushed_valid[buf] = true;
@@ -288,7 +276,6 @@ int bnv_exchange_push(bnv_exchange_t* ex, void* stream) {
   BNV_LAUNCH_CHECK("insert_inbox_kernel");
   BNV_CUDA(cudaEventRecord(ex->upserted, ex->side));
   ex->any_upsert = true;
-  ex->frame_open = false;
   return BNV_OK;
 }
 
@@ -307,8 +294,6 @@ int bnv_exchange_destroy(bnv_exchange_t* ex) {
     if (r != ex->rank && ex->peers.base[r]) cudaIpcCloseMemHandle(ex->peers.base[r]);
   if (ex->block) cudaFree(ex->block);
   if (ex->scratch) cudaFree(ex->scratch);
-  ex->map->d.halo = nullptr;
-  ex->map->d.halo_cap = 0;
   for (int i = 0; i < 2; ++i) {
     if (ex->halo[i]) cudaFree(ex->halo[i]);
     if (ex->pushed[i]) cudaEventDestroy(ex->pushed[i]);

@@ -27,13 +27,19 @@ constexpr int kNWG = 4;                       // row warpgroups (= chains = TMEM
 constexpr int kThreads = kNWG * 128;
 constexpr uint32_t kOnes = 0x3C003C00u;       // fp16x2 {1.0, 1.0}: tcnn pads the input with ones
 
-struct alignas(16) Smem {
+struct alignas(16) Smem {         // plain forward, decode, G table: the chain's barriers only
   TcShared<kNWG> sh;
-  int32_t slot[8][kThreads];   // encode: scratch row of (this thread's point, corner k); thread-private, [k][tid]
+};
+struct alignas(16) SmemEnc {      // encode
+  TcShared<kNWG> sh;
+  int32_t slot[8][kThreads];      // dense scratch row of (this thread's point, corner k); thread-private, [k][tid]
+  float4 rec[2][2][kThreads];     // point records of this / the next tile (cp.async double buffer), [buf][half][tid]
 };
 
-__device__ __forceinline__ uint8_t* weights_smem(uint8_t* smem) { return smem + ((sizeof(Smem) + 127) / 128) * 128; }
-static size_t smem_bytes(int in_pad) { return ((sizeof(Smem) + 127) / 128) * 128 + weight_image(in_pad).bytes; }
+template <class S>
+__device__ __forceinline__ uint8_t* weights_smem(uint8_t* smem) { return smem + ((sizeof(S) + 127) / 128) * 128; }
+template <class S>
+static size_t smem_bytes(int in_pad) { return ((sizeof(S) + 127) / 128) * 128 + weight_image(in_pad).bytes; }
 
 static int sm_count() {
   int dev = 0, sms = 148;
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
                                                                       float* __restrict__ y) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem<Smem>(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t n_tiles = (n + 127) / 128;
   const int64_t stride = (int64_t)gridDim.x * kNWG;
@@ -107,6 +113,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc_kernel(const uint8
   tc_teardown<kNWG>(S.sh);
 }
 
+// ---- cp.async (LDGSTS): global -> shared memory without staging registers -------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// 16 / 4 bytes, zero-filled when !pred (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool pred) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(pred ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gsrc, bool pred) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(pred ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+
 // ---- fused encode -----------------------------------------------------------------------------------
 // Work unit = (128-point tile, corner).  Chain j of J processes the contiguous unit range
 // [U j / J, U (j + 1) / J): whole tiles in the middle, partial tiles (a corner sub-range) at both ends, so
@@ -132,9 +153,9 @@ __device__ __forceinline__ void enc_input(int k, const float (&cc)[3], const flo
 
 __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, const uint8_t* __restrict__ gW, int w_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
-  Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
-  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5;
+  SmemEnc& S = *reinterpret_cast<SmemEnc*>(smem);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem<SmemEnc>(smem), gW, w_bytes);
+  const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5, tid = threadIdx.x;
   const GeomDev& g = m.g;
   const int64_t n_rec = m.ctr[4];                       // point records written by frame_prepass_kernel
   const int64_t n_units = ((n_rec + 127) / 128) * 8;
@@ -142,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
   const int64_t u_end = n_units * (chain + 1) / n_chains;
   int32_t pend_row = -1;
   bool pending = false;                                // an output layer is in flight / unread in D_out
-  int flip = 0;
+  int flip = 0, buf = 0;
   auto drain = [&]() {
     if (pending) {
       float y[8];
@@ -151,18 +172,29 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
       pending = false;
     }
   };
-  for (int64_t u = n_units * chain / n_chains; u < u_end;) {
+  // point record of tile `tile` -> shared memory (32 bytes per thread, no registers held across the chain)
+  auto fetch_record = [&](int64_t tile, int b) {
+    const int64_t idx = tile * 128 + r;
+    const bool have = idx < n_rec;
+    const float4* r4 = reinterpret_cast<const float4*>(m.prec + (size_t)(have ? idx : 0) * 8);
+    cp_async16_zfill(&S.rec[b][0][tid], r4, have);
+    cp_async16_zfill(&S.rec[b][1][tid], r4 + 1, have);
+    cp_async_commit();
+  };
+  BNV_PROF_MARK(p_life);
+  int64_t u = n_units * chain / n_chains;
+  if (u < u_end) fetch_record(u >> 3, buf);
+  while (u < u_end) {
+    BNV_PROF_MARK(p_pre);
     const int64_t tile = u >> 3;
     const int k0 = (int)(u & 7);
     const int k1 = (int)(u_end - u < (int64_t)(8 - k0) ? k0 + (u_end - u) : 8);
     u += k1 - k0;
     const int64_t idx = tile * 128 + r;
-    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
-    if (idx < n_rec) {
-      const float4* r4 = reinterpret_cast<const float4*>(m.prec + (size_t)idx * 8);
-      ra = __ldg(r4);
-      rb = __ldg(r4 + 1);
-    }
+    cp_async_wait_all();
+    const float4 ra = S.rec[buf][0][tid], rb = S.rec[buf][1][tid];     // zeros past the last record
+    if (u < u_end) fetch_record(tile + 1, buf ^ 1);                     // lands while this tile's corners run
+    buf ^= 1;
     const float cc[3] = {ra.x, ra.y, ra.z};
     float fl[3], ce[3];
 #pragma unroll
@@ -175,16 +207,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
     // corners of this chain's unit range that this rank owns (the prepass stored the ownership mask)
     const uint32_t range = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
     const uint32_t own = (idx < n_rec ? (uint32_t)__float_as_int(rb.z) : 0u) & range;
-    // dense scratch rows of the owned corners: 8 independent table reads in flight (high word of ftable[flat])
+    // dense scratch rows of the owned corners: 8 independent table reads (high word of ftable[flat]) whose results
+    // are parked in shared memory in the shadow of the tile's first MLP round, where they are first needed
+    int32_t rows[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      int32_t row = -1;
+      rows[k] = -1;
       if ((own >> k) & 1u) {
         float nb[3];
         corner_of(k, fl, ce, nb);
-        row = scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]);   // rule A5
+        rows[k] = scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]);   // rule A5
       }
-      S.slot[k][threadIdx.x] = row;
     }
     // corners to run: all of [k0, k1) on one GPU; in the tile shard only those somebody here owns
     uint32_t live = range;
@@ -204,13 +237,22 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
       chain_stage<8>(c, in);
       chain_begin<8>(c);
     }
+    BNV_PROF_ADD(9, p_pre);
+    bool first = true;
 #pragma unroll 1
     for (uint32_t rem = live; rem;) {
       const int k = __ffs(rem) - 1;
       rem &= rem - 1;
       const bool has_next = rem != 0;
       chain_hidden<8>(
-          c, [&]() { drain(); },
+          c,
+          [&]() {
+            drain();                      // reads the PREVIOUS tile's row from pend_row (a register): safe to overwrite
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) S.slot[j][tid] = rows[j];
+            }
+          },
           [&]() {
             if (has_next) {
               uint32_t in[8];
@@ -218,12 +260,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
               chain_stage<8>(c, in);
             }
           });
+      first = false;
       chain_finish<8>(c, has_next);
       pending = true;
-      pend_row = S.slot[k][threadIdx.x];
+      pend_row = S.slot[k][tid];
     }
   }
   drain();
+  cp_async_wait_all();
+  BNV_PROF_ADD(10, p_life);
   tc_teardown<kNWG>(S.sh);
 }
 
@@ -233,22 +278,36 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
 // a corner row is then 4 gathered words + 6 selected words + 6 constants.  Keeping it out of the register
 // file leaves room for the 96 transient registers of the hidden-layer epilogue (no spills) and lets the
 // 8-corner loop stay rolled (8x less code, no instruction-cache misses).
+//
+// Latency: a query needs two dependent scattered reads per corner (table entry -> packed feature row) that
+// hit L2 at best.  They are software-pipelined ONE TILE AHEAD with cp.async (global -> shared memory without
+// registers, zero-fill for misses): while tile i runs its 8 corners through the chain, the table entries of tile
+// i + 1 are fetched during corner 1, its feature rows and weights during corner 7 (by then every staging slot of
+// tile i has been consumed), its per-axis words are computed in the shadow of the last layer of corner 7.  The
+// chain never waits for a gather (profiles/r2a: the one-corner-ahead register prefetch left 900 of 3500 cycles per
+// corner exposed in the staging shadow and 1800 per corner in the per-tile precompute).
 struct DecState {
   uint32_t w_ls[3][2][kThreads];   // fp16x2 {l, sin l}
   uint32_t w_c1[3][2][kThreads];   // fp16x2 {cos l, 1}
   float t[3][2][kThreads];         // 1 - |l|
   int32_t ts[3][2][kThreads];      // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
-  int32_t slot[8][kThreads];       // table lookup of corner k (_query_tensor)
+  uint4 feat[8][kThreads];         // packed fp16x8 feature row of corner k (zeros on a miss), cp.async target
+  float wt[8][kThreads];           // fusion weight of corner k (0 on a miss), cp.async target
+  int32_t slot[8][kThreads];       // table entry of corner k of the NEXT tile (_query_tensor), cp.async target
+  float nq[3][kThreads];           // voxel-unit coordinates of the NEXT tile's query
 };
+
+__device__ const int32_t g_kempty_word = kEmpty;   // source of the table "lookup" of an out-of-grid corner
 
 __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint4* __restrict__ packed,
                                                                  const uint8_t* __restrict__ gW, int w_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
-  DecState& Q = *reinterpret_cast<DecState*>(weights_smem(smem) + ((w_bytes + 127) / 128) * 128);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem<Smem>(smem), gW, w_bytes);
+  DecState& Q = *reinterpret_cast<DecState*>(weights_smem<Smem>(smem) + ((w_bytes + 127) / 128) * 128);
   const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
+  const int64_t stride = (int64_t)gridDim.x * kNWG;
   const GeomDev& g = m.g;
   constexpr int32_t kOut = INT_MIN;
   const bool has_prior = a.tsdf != nullptr;
@@ -259,21 +318,85 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     const int32_t px = Q.ts[0][corner_sx(k)][tid], py = Q.ts[1][corner_sy(k)][tid], pz = Q.ts[2][corner_sz(k)][tid];
     return (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
   };
-  auto gather = [&](int k, uint4& f, float& w) {                                         // D3
-    f = make_uint4(0, 0, 0, 0);
-    w = 0.f;
-    const int32_t s = Q.slot[k][tid];
-    if (s >= 0 && s < a.n_rows) {
-      f = __ldg(packed + s);
-      w = __ldg(a.weights_rows + s);
-    }
-  };
-  auto stage_corner = [&](int k, const uint4& f) {
+  auto stage_corner = [&](int k) {
     const int sx = corner_sx(k), sy = corner_sy(k), sz = corner_sz(k);
+    const uint4 f = Q.feat[k][tid];
     const uint32_t in[16] = {f.x, f.y, f.z, f.w,
                              Q.w_ls[0][sx][tid], Q.w_c1[0][sx][tid], Q.w_ls[1][sy][tid], Q.w_c1[1][sy][tid],
                              Q.w_ls[2][sz][tid], Q.w_c1[2][sz][tid], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
     chain_stage<16>(c, in);
+  };
+  // query coordinates of tile `tile` -> Q.nq (zeros past the end)
+  auto load_coords = [&](int64_t tile) {
+    const int64_t q = tile * 128 + r;
+    float cq[3] = {0.f, 0.f, 0.f};
+    if (tile < n_tiles && q < a.n_queries) query_coords(m, a, q, cq);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) Q.nq[d][tid] = cq[d];
+  };
+  // the 8 table entries of the query in Q.nq -> Q.slot (D3, _query_tensor): 8 x 4-byte cp.async
+  auto fetch_slots = [&](bool live) {
+    int32_t tab[3][2];
+    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float cq = Q.nq[d][tid];
+      const float nbv[2] = {floorf(cq), ceilf(cq)};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int iv = (int)nbv[s];
+        tab[d][s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int32_t tx = tab[0][corner_sx(k)], ty = tab[1][corner_sy(k)], tz = tab[2][corner_sz(k)];
+      const bool in_grid = tx != kOut && ty != kOut && tz != kOut;
+      const int32_t* src = in_grid ? m.table + ((int64_t)tx + ty + tz) : &g_kempty_word;
+      cp_async4(&Q.slot[k][tid], src);
+    }
+    cp_async_commit();
+  };
+  // feature rows + fusion weights of the 8 corners in Q.slot -> Q.feat / Q.wt (zeros on a miss)
+  auto fetch_rows = [&]() {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int32_t s = Q.slot[k][tid];
+      const bool hit = s >= 0 && s < a.n_rows;
+      cp_async16_zfill(&Q.feat[k][tid], packed + (hit ? s : 0), hit);
+      cp_async4_zfill(&Q.wt[k][tid], a.weights_rows + (hit ? s : 0), hit);
+    }
+    cp_async_commit();
+  };
+  // everything that depends on one axis only, for the query in Q.nq (D1, D2, D6)
+  auto axis_state = [&]() {
+    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float cq = Q.nq[d][tid];
+      const float nbv[2] = {floorf(cq), ceilf(cq)};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float l = __fsub_rn(cq, nbv[s]);                                           // D1
+        float sn, cs;
+        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
+        Q.w_ls[d][s][tid] = pack_f16x2(l, sn);
+        Q.w_c1[d][s][tid] = pack_f16x2(cs, 1.0f);
+        Q.t[d][s][tid] = __fsub_rn(1.f, fabsf(l));
+        int32_t ts = kOut;
+        if (has_prior) {                                                                 // grid_sample(nearest), D6
+          float t = __fdiv_rn(nbv[s], a.nm1[d]);
+          t = __fmul_rn(t, 2.f);
+          t = __fsub_rn(t, 1.f);
+          t = __fadd_rn(t, 1.f);
+          t = __fmul_rn(t, 0.5f);
+          t = __fmul_rn(t, a.tm1[d]);
+          const float rr = nearbyintf(t);
+          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ts = (int)rr * pstride[d];
+        }
+        Q.ts[d][s][tid] = ts;
+      }
+    }
   };
   // the query whose last corner is still in D_out
   bool pending = false, p_live = false;
@@ -294,80 +417,39 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     }
   };
   BNV_PROF_MARK(p_life);
-  for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
+  int64_t tile = (int64_t)blockIdx.x * kNWG + wg;
+  if (tile < n_tiles) {          // pipeline prologue: the first tile's lookups, synchronously
+    load_coords(tile);
+    fetch_slots(tile * 128 + r < a.n_queries);
+    axis_state();
+    cp_async_wait_all();
+    fetch_rows();
+  }
+  for (; tile < n_tiles; tile += stride) {
     BNV_PROF_MARK(p_pre);
     const int64_t q = tile * 128 + r;
     const bool live = q < a.n_queries;
-    float cq[3] = {0.f, 0.f, 0.f};
-    if (live) query_coords(m, a, q, cq);
-    // ---- once per query: everything that depends on one axis only ---------------------------------
-    int32_t tab[3][2];                // voxel index * table stride of this axis, or INT_MIN when outside the grid
-    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
-    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float nbv[2] = {floorf(cq[d]), ceilf(cq[d])};
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const float l = __fsub_rn(cq[d], nbv[s]);                                        // D1
-        float sn, cs;
-        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
-        Q.w_ls[d][s][tid] = pack_f16x2(l, sn);
-        Q.w_c1[d][s][tid] = pack_f16x2(cs, 1.0f);
-        Q.t[d][s][tid] = __fsub_rn(1.f, fabsf(l));
-        const int iv = (int)nbv[s];
-        tab[d][s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
-        int32_t ts = kOut;
-        if (has_prior) {                                                                 // grid_sample(nearest), D6
-          float t = __fdiv_rn(nbv[s], a.nm1[d]);
-          t = __fmul_rn(t, 2.f);
-          t = __fsub_rn(t, 1.f);
-          t = __fadd_rn(t, 1.f);
-          t = __fmul_rn(t, 0.5f);
-          t = __fmul_rn(t, a.tm1[d]);
-          const float rr = nearbyintf(t);
-          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ts = (int)rr * pstride[d];
-        }
-        Q.ts[d][s][tid] = ts;
-      }
-    }
-    float wsum = 0.f;
+    cp_async_wait_all();                      // this tile's feature rows / weights (issued a whole corner ago)
+    float wsum = 0.f, minw = 3.0e38f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float w = weight_of(k);
       wsum = k == 0 ? w : __fadd_rn(wsum, w);                                            // D2 normaliser
-    }
-    // ---- 8 independent table lookups in flight (_query_tensor, D3) ---------------------------------
-    int32_t slot0 = kEmpty;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int32_t tx = tab[0][corner_sx(k)], ty = tab[1][corner_sy(k)], tz = tab[2][corner_sz(k)];
-      int32_t sl = kEmpty;
-      if (tx != kOut && ty != kOut && tz != kOut) sl = __ldg(m.table + ((int64_t)tx + ty + tz));
-      Q.slot[k][tid] = sl;
-      if (k == 0) slot0 = sl;
-    }
-    uint4 f_nxt = make_uint4(0, 0, 0, 0);
-    float w_nxt = 0.f;
-    if (slot0 >= 0 && slot0 < a.n_rows) {
-      f_nxt = __ldg(packed + slot0);
-      w_nxt = __ldg(a.weights_rows + slot0);
+      minw = fminf(minw, Q.wt[k][tid]);                                                  // D3
     }
     // the previous query's last corner has been in flight during all of the above
     drain();
-    float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
-    stage_corner(0, f_nxt);
+    float sdf = 0.f, dsum = 0.f;
+    stage_corner(0);
     chain_begin<16>(c);
     BNV_PROF_ADD(9, p_pre);
-    float w_cur = w_nxt;
+    const bool has_next_tile = tile + stride < n_tiles;
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
-      minw = fminf(minw, w_cur);                                                         // D3
       chain_hidden<16>(
           c,
           [&]() {
-            // shadow of the second layer: issue the next corner's gather, blend the previous corner
-            if (k < 7) gather(k + 1, f_nxt, w_nxt);
+            // shadow of the second layer: blend the previous corner; feed the next tile's pipeline
             if (k > 0) {
               float y[1];
               chain_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
@@ -375,13 +457,27 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
               sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                // D4, D5
               if (has_prior) dsum = __fadd_rn(dsum, __fmul_rn(prior_of(k - 1), wn));     // D6
             }
+            if (k == 0) {
+              load_coords(tile + stride);
+            } else if (k == 1) {
+              fetch_slots(has_next_tile && (tile + stride) * 128 + r < a.n_queries);
+            } else if (k == 7) {
+              cp_async_wait_all();            // the next tile's table entries (issued six corners ago)
+              fetch_rows();                   // every staging slot of this tile has been consumed
+            }
           },
           [&]() {
-            // shadow of the third layer: the gather has landed -> stage the next corner's row
-            if (k < 7) stage_corner(k + 1, f_nxt);
+            // shadow of the third layer: stage the next corner's row; after the last staging the per-axis words
+            // are free for the next tile (corner 7's blend weight and prior are saved first)
+            if (k < 7) {
+              stage_corner(k + 1);
+            } else {
+              p_wn = __fdiv_rn(weight_of(7), wsum);
+              p_dl = has_prior ? prior_of(7) : 0.f;
+              axis_state();
+            }
           });
       chain_finish<16>(c, k < 7);
-      w_cur = w_nxt;
     }
     // corner 7 is in flight: finish this query at the top of the next tile (or after the loop)
     pending = true;
@@ -390,10 +486,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     p_sdf = sdf;
     p_dsum = dsum;
     p_minw = minw;
-    p_wn = __fdiv_rn(weight_of(7), wsum);
-    p_dl = has_prior ? prior_of(7) : 0.f;
   }
   drain();
+  cp_async_wait_all();
   BNV_PROF_ADD(10, p_life);
   tc_teardown<kNWG>(S.sh);
 }
@@ -404,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtable_tc_kernel(const uint4* __r
                                                                  float* __restrict__ G) {
   extern __shared__ __align__(128) uint8_t smem[];
   Smem& S = *reinterpret_cast<Smem*>(smem);
-  RowChain c = tc_setup<kNWG>(S.sh, weights_smem(smem), gW, w_bytes);
+  RowChain c = tc_setup<kNWG>(S.sh, weights_smem<Smem>(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127;
   const int64_t total = (n_rows + 1) * 27;                       // voxel n_rows = the miss voxel
   const int64_t n_tiles = (total + 127) / 128;
@@ -480,7 +575,7 @@ static int set_smem(Kern k, size_t bytes) {
 }
 
 int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s) {
-  const size_t smem = smem_bytes(mlp->in_pad);
+  const size_t smem = smem_bytes<Smem>(mlp->in_pad);
   const int grid = grid_for((n + 127) / 128);
   if (mlp->n_in == 6) {
     int rc = set_smem(mlp_forward_tc_kernel<6, 8, 8>, smem);
@@ -497,7 +592,7 @@ int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t
 
 int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s) {
   // the record count lives on the device (ctr[4]); the grid is sized for the most the prepass can have written
-  const size_t smem = smem_bytes(enc->in_pad);
+  const size_t smem = smem_bytes<SmemEnc>(enc->in_pad);
   int rc = set_smem(encode_chain_kernel, smem);
   if (rc) return rc;
   const int grid = grid_for(((max_records + 127) / 128) * 8);        // units = (tile, corner)
@@ -507,7 +602,7 @@ int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp
 }
 
 int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
-  const size_t smem = ((smem_bytes(dec->in_pad) + 127) / 128) * 128 + sizeof(DecState);
+  const size_t smem = ((smem_bytes<Smem>(dec->in_pad) + 127) / 128) * 128 + sizeof(DecState);
   int rc = set_smem(decode_tc_kernel, smem);
   if (rc) return rc;
   decode_tc_kernel<<<grid_for((a.n_queries + 127) / 128), kThreads, smem, s>>>(
@@ -517,7 +612,7 @@ int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_m
 }
 
 int bnv_internal_gtable_chain(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s) {
-  const size_t smem = smem_bytes(dec->in_pad);
+  const size_t smem = smem_bytes<Smem>(dec->in_pad);
   int rc = set_smem(gtable_tc_kernel, smem);
   if (rc) return rc;
   const int64_t tiles = ((n_rows + 1) * 27 + 127) / 128;

@@ -7,13 +7,14 @@ B200-side extension the north star asks for: ownership is a pure function of the
                                                                     balanced for planar surfaces
                                                                     along any axis)
 
-Every rank receives the whole depth frame and runs the same fused encode kernel, which drops the
-(point, corner) rows whose voxel it does not own *before* the MLP, so the tensor-core work divides
-by `world` while per-voxel means stay identical to the single-GPU result (all rows of a voxel go to
-its one owner: no cross-GPU reduction).  A query's 8 corners are floor/ceil voxels and meshlize samples
-id +- 0.5, so a rank also needs the one-voxel shell around its bricks: after each frame the ranks
-all-gather the records of the brick-shell voxels they integrated (ONE collective per frame, fixed-capacity buffer with the
-count in its header) and upsert the ones they need as halo copies.
+Every rank receives the whole depth frame and runs the same kernels, which drop the (point, corner)
+rows whose voxel the rank does not own *before* the MLP (the prepass compacts only the points with an
+owned corner), so the tensor-core work divides by `world` while per-voxel means stay identical to the
+single-GPU result (all rows of a voxel go to its one owner: no cross-GPU reduction).  A query's 8
+corners are floor/ceil voxels and meshlize samples id +- 0.5, so a rank also needs the one-voxel shell
+around its bricks: the ranks all-gather the records of the brick-shell voxels they integrated (ONE
+collective per exchange epoch -- every K frames and before reads -- fixed-capacity buffer with the count
+in its header) and upsert the ones they need as halo copies.
 
 The buffer protocol and the selection rule live in plain numpy functions so that the N > 1 logic is
 covered on CPU with gloo (tests/test_dist_cpu.py); the GPU path calls the same rule inside
@@ -107,10 +108,19 @@ def needed_by(flat, n_xyz, world, brick_log2):
 
 
 class TileShardedFusion:
-    """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank."""
+    """GPU driver of the tile shard: wraps a SparseVolume + LitFusionPointNet of this rank.
 
-    def __init__(self, volume, model, rank, world, brick_log2=4, halo_capacity=1 << 16, group=None, overlap=True,
-                 exchange="nccl"):
+    Per frame the rank does exactly what a single GPU does (ONE library call: prepass -> encoder MLP -> finalize),
+    restricted to the voxels it owns.  Halo copies of foreign voxels are only ever read (decode, query), so the
+    boundary exchange is decoupled from the frame loop: finalize remembers the brick-shell voxels it integrates, and
+    every `exchange_every` frames -- and whenever the map is read (`synchronize`, called by the volume's read paths) --
+    ONE exchange epoch ships their current values: pack kernel on the fusing stream, then on a side stream either one
+    NCCL all-gather + upsert (exchange="nccl", the collective the north star names) or sender-routed stores into the
+    peers' inboxes over NVLink (exchange="p2p", csrc/bnv_p2p.cu).  All ranks must fuse / read in lockstep (they do:
+    every rank sees every frame)."""
+
+    def __init__(self, volume, model, rank, world, brick_log2=5, halo_capacity=1 << 17, group=None, exchange="nccl",
+                 exchange_every=16):
         import torch
         from . import _lib
         self.torch, self._lib = torch, _lib
@@ -118,25 +128,28 @@ class TileShardedFusion:
         self.rank, self.world, self.brick_log2 = int(rank), int(world), int(brick_log2)
         self.capacity = int(halo_capacity)
         self.group = group
-        words = HEADER_WORDS + self.capacity * RECORD_WORDS
-        dev = volume.device
-        # two buffer pairs: the exchange of frame f runs on a side stream while frame f + 1 is fused
-        self.halo = [torch.zeros(words, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.gathered = [torch.zeros(words * self.world, dtype=torch.int32, device=dev) for _ in range(2)]
-        self.done = [None, None]                 # side-stream event: exchange that last used pair i finished
-        self.flip = 0
-        self.overlap = bool(overlap) and self.world > 1
-        self.side = torch.cuda.Stream(device=dev) if self.overlap else None
-        volume.set_shard(self.rank, self.world, self.brick_log2)
-        volume._halo_sync = self.synchronize     # SparseVolume reads (to_tensor, decode) wait for the halo
-        self._attach(0)
-        # exchange="p2p": EXPERIMENTAL peer-memory routing (csrc/bnv_p2p.cu, not yet validated on hardware);
-        # the default is the all-gather the north star names
+        self.exchange_every = max(1, int(exchange_every))
         self.exchange = exchange
         self._ex = None
-        if exchange == "p2p" and self.world > 1:
+        self._since = 0                          # frames fused since the last exchange epoch
+        self.epochs = 0
+        dev = volume.device
+        volume.set_shard(self.rank, self.world, self.brick_log2)
+        if self.world == 1:
+            return                               # nothing to exchange: no halo bookkeeping at all
+        lib = volume._lib
+        _lib.check(lib.bnv_map_halo_enable(volume._handle, self.capacity), "bnv_map_halo_enable")
+        volume._halo_sync = self.synchronize     # SparseVolume reads (to_tensor, decode, query) flush + join the exchange
+        if exchange == "nccl":
+            words = HEADER_WORDS + self.capacity * RECORD_WORDS
+            # two buffer pairs: epoch e runs on the side stream while the frames of epoch e + 1 are fused
+            self.send = [torch.zeros(words, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.gathered = [torch.zeros(words * self.world, dtype=torch.int32, device=dev) for _ in range(2)]
+            self.done = [None, None]             # side-stream event: the epoch that last used pair i has been upserted
+            self.flip = 0
+            self.side = torch.cuda.Stream(device=dev)
+        elif exchange == "p2p":
             import torch.distributed as dist
-            lib = volume._lib
             ex = C.c_void_p()
             _lib.check(lib.bnv_exchange_create(C.byref(ex), volume._handle, self.capacity), "bnv_exchange_create")
             mine = (C.c_ubyte * 64)()
@@ -147,62 +160,57 @@ class TileShardedFusion:
             _lib.check(lib.bnv_exchange_connect(ex, blob), "bnv_exchange_connect")
             dist.barrier(group=group)
             self._ex = ex
-        elif exchange != "nccl":
+        else:
             raise ValueError("exchange must be 'nccl' or 'p2p'")
 
-    def _attach(self, i):
-        v = self.volume
-        self._lib.check(v._lib.bnv_map_set_halo_buffer(v._handle, self._lib.ptr(self.halo[i]), self.capacity),
-                        "bnv_map_set_halo_buffer")
-
+    # ---- per frame: the single-GPU call, restricted to owned voxels by the kernels ------------------------------
     def fuse_depth_frame(self, depth_mm, K, T_wc, max_depth=3.0, stats=None, navg=None):
-        """Fuse one frame into this rank's tiles, then exchange the boundary voxels (ONE all-gather).
-
-        Integration only ever touches voxels this rank owns, halo copies are only read by decode: the
-        all-gather + halo upsert of frame f therefore runs on a side stream, overlapped with the fusion of
-        frame f + 1; `synchronize()` (called by the volume's read paths) joins the two streams."""
-        self._fuse(lambda: self.model.fuse_depth_frame(self.volume, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg))
+        self.model.fuse_depth_frame(self.volume, depth_mm, K, T_wc, max_depth, stats=stats, navg=navg)
+        self._frame_done()
 
     def fuse_depth_frame_host(self, depth_mm_host, K, T_wc, max_depth=3.0, stats_host=None, next_depth_mm_host=None):
-        """Same from a (pinned) host frame: H2D + fuse + D2H of the statistics in one library call
-        (LitFusionPointNet.fuse_depth_frame_host), then the boundary exchange."""
-        self._fuse(lambda: self.model.fuse_depth_frame_host(self.volume, depth_mm_host, K, T_wc, max_depth,
-                                                            stats_host=stats_host, next_depth_mm_host=next_depth_mm_host))
+        self.model.fuse_depth_frame_host(self.volume, depth_mm_host, K, T_wc, max_depth, stats_host=stats_host,
+                                         next_depth_mm_host=next_depth_mm_host)
+        self._frame_done()
 
-    def _fuse(self, fuse_call):
-        import torch.distributed as dist
-        torch = self.torch
-        v, lib = self.volume, self._lib
-        if self._ex is not None:                 # peer-memory exchange: buffers, routing and waits live in the library
-            lib.check(v._lib.bnv_exchange_begin_frame(self._ex, v._stream()), "bnv_exchange_begin_frame")
-            fuse_call()
+    def _frame_done(self):
+        self._since += 1
+        if self.world > 1 and self._since >= self.exchange_every:
+            self.exchange_now()
+
+    # ---- one exchange epoch -----------------------------------------------------------------------------------------
+    def exchange_now(self):
+        """Ship the shell voxels integrated since the last epoch (collective: every rank must call it at the same frame)."""
+        if self.world == 1:
+            return
+        torch, lib, v = self.torch, self._lib, self.volume
+        self._since = 0
+        self.epochs += 1
+        if self._ex is not None:
             lib.check(v._lib.bnv_exchange_push(self._ex, v._stream()), "bnv_exchange_push")
             return
+        import torch.distributed as dist
         i = self.flip
         main = torch.cuda.current_stream(v.device)
-        if self.done[i] is not None:             # the exchange two frames ago used this buffer pair
+        if self.done[i] is not None:             # the epoch two back used this buffer pair
             main.wait_event(self.done[i])
-        self._attach(i)
-        lib.check(v._lib.bnv_map_halo_begin(v._handle, v._stream()), "bnv_map_halo_begin")
-        fuse_call()
-        if self.world > 1:
-            if not self.overlap:
-                dist.all_gather_into_tensor(self.gathered[i], self.halo[i], group=self.group)   # the one collective
-                lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered[i]), self.world, self.capacity,
-                                                     v._stream()), "bnv_map_insert_halo")
-            else:
-                fused = main.record_event()
-                with torch.cuda.stream(self.side):
-                    self.side.wait_event(fused)
-                    dist.all_gather_into_tensor(self.gathered[i], self.halo[i], group=self.group)   # the one collective
-                    lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered[i]), self.world,
-                                                         self.capacity, C.c_void_p(self.side.cuda_stream)),
-                              "bnv_map_insert_halo")
-                    self.done[i] = self.side.record_event()
+        lib.check(v._lib.bnv_map_halo_pack(v._handle, lib.ptr(self.send[i]), self.capacity, v._stream()), "bnv_map_halo_pack")
+        packed = main.record_event()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(packed)
+            dist.all_gather_into_tensor(self.gathered[i], self.send[i], group=self.group)      # the one collective
+            lib.check(v._lib.bnv_map_insert_halo(v._handle, lib.ptr(self.gathered[i]), self.world, self.capacity,
+                                                 C.c_void_p(self.side.cuda_stream)), "bnv_map_insert_halo")
+            self.done[i] = self.side.record_event()
         self.flip ^= 1
 
     def synchronize(self):
-        """the current stream waits for every halo exchange issued so far"""
+        """Flush the frames fused since the last epoch and make the current stream wait for every exchange issued so
+        far (collective; called by the volume's read paths)."""
+        if self.world == 1:
+            return
+        if self._since > 0:
+            self.exchange_now()
         if self._ex is not None:
             self._lib.check(self.volume._lib.bnv_exchange_join(self._ex, self.volume._stream()), "bnv_exchange_join")
             return
@@ -217,10 +225,12 @@ class TileShardedFusion:
         return (c.sum(dim=1) % self.world) == self.rank
 
     def detach(self):
+        if self.world == 1:
+            return
         self.synchronize()
         self.volume._halo_sync = None
+        self.torch.cuda.synchronize()
         if self._ex is not None:
-            self.torch.cuda.synchronize()
             self._lib.check(self.volume._lib.bnv_exchange_destroy(self._ex), "bnv_exchange_destroy")
             self._ex = None
-        self._lib.check(self.volume._lib.bnv_map_set_halo_buffer(self.volume._handle, None, 0), "detach halo")
+        self._lib.check(self.volume._lib.bnv_map_halo_enable(self.volume._handle, 0), "bnv_map_halo_enable(0)")

@@ -414,7 +414,19 @@ class SparseVolume:
         torch.save(out_dict, path + "_sparse_volume.pth")
 
     def load(self, path):
-        volume = torch.load(path, map_location=self.device)
+        """sparse_volume.py:863-892.  Reads a `*_sparse_volume.pth` written by this class or by the reference's own
+        SparseVolume.save (a pickled dict holding numpy scalars next to the tensors: weights_only=False, like the
+        torch 1.10 `torch.load(path)` of the reference).  The voxels are upserted into the device map, so -- unlike
+        the reference, which only rebuilds the tensor indexer -- query / integrate work on a loaded volume too."""
+        volume = torch.load(path, map_location=self.device, weights_only=False)
+        for k in ("features", "weights", "num_hits", "active_coordinates"):
+            if k not in volume:
+                raise KeyError(f"{path}: not a SparseVolume checkpoint (missing '{k}')")
+        if abs(float(volume.get("voxel_size", self.voxel_size)) - float(self.voxel_size)) > 1e-12:
+            raise ValueError(f"{path}: checkpoint voxel_size {volume['voxel_size']} != volume voxel_size {self.voxel_size}")
+        n = volume["active_coordinates"].shape[0]
+        if n > self._pool:
+            raise RuntimeError(f"{path}: {n} voxels exceed this volume's pool capacity {self._pool}")
         self.reset()
         feats = volume["features"].detach().float()
         self.insert(volume["active_coordinates"], feats, volume["weights"], volume["num_hits"])

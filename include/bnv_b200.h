@@ -92,34 +92,33 @@ int bnv_map_status(bnv_map_t* map, void* stream);
  * Encode calls drop (point, corner) rows whose voxel another rank owns.  world = 1 disables. */
 int bnv_map_set_shard(bnv_map_t* map, int rank, int world, int brick_log2);
 
-/* Halo exchange of the tile shard (no reference equivalent: the reference is single-GPU).  A query's
- * 8 corners are floor/ceil voxels and meshlize samples id +- 0.5, so a rank also needs the one-voxel
- * shell around each of its bricks.  With a halo buffer attached, bnv_fuse_frame / bnv_fuse_points
- * append one record per voxel they integrated that lies on the outer shell of its brick:
+/* Boundary (halo) exchange of the tile shard (no reference equivalent: the reference is single-GPU).  A query's
+ * 8 corners are floor/ceil voxels and meshlize samples id +- 0.5, so a rank also needs the one-voxel shell around each
+ * of its bricks.  Halo copies are only ever READ (decode, query), never integrated into, so the exchange is decoupled
+ * from the frame loop: with bnv_map_halo_enable, bnv_fuse_frame / bnv_fuse_points remember -- once per voxel -- every
+ * voxel they integrate that lies on the outer shell of its brick; an exchange EPOCH (every K frames, and before the map
+ * is read) turns that list into records with the voxels' current values
  *     struct { int32 flat_id; float weight; float feat[8]; }   (40 bytes)
- * into buf_dev = [int32 count, int32 pad[9], records...] (capacity records).  The caller all-gathers
- * the ranks' buffers (one NCCL all-gather per frame) and hands the result to bnv_map_insert_halo,
-  * which upserts the records of the other ranks that touch one of this rank's bricks.
- * bnv_map_halo_begin resets the count (stream-ordered).  buf_dev == NULL detaches. */
+ * in buf_dev = [int32 count, int32 pad[9], records...] (bnv_map_halo_pack, which also re-arms the list).  The caller
+ * all-gathers the ranks' buffers (ONE NCCL all-gather per epoch) and hands the result to bnv_map_insert_halo, which
+ * upserts the records of the other ranks that touch one of this rank's bricks.  capacity_records = 0 disables. */
 #define BNV_HALO_RECORD_BYTES 40
-int bnv_map_set_halo_buffer(bnv_map_t* map, void* buf_dev, int64_t capacity_records);
-int bnv_map_halo_begin(bnv_map_t* map, void* stream);
+int bnv_map_halo_enable(bnv_map_t* map, int64_t capacity_records);
+int bnv_map_halo_pack(bnv_map_t* map, void* buf_dev, int64_t capacity_records, void* stream);
 int bnv_map_insert_halo(bnv_map_t* map, const void* gathered_dev, int world, int64_t capacity_records,
                         void* stream);
 
-/* EXPERIMENTAL peer-memory variant of the halo exchange (csrc/bnv_p2p.cu; not yet validated on hardware, the
- * all-gather path above is the default): the sender routes each boundary record straight into the inbox of
- * the ranks that need it (stores over NVLink into cudaIpc-mapped memory), the receiver upserts its inbox on a
- * side stream once every peer's frame sequence number has arrived.  Usage, one process per GPU:
- *   bnv_map_set_shard, bnv_exchange_create, bnv_exchange_handle (64 bytes), all-gather the handles by any
- *   transport, bnv_exchange_connect; then per frame, on every rank: bnv_exchange_begin_frame (attaches and
- *   resets this frame's record buffer), bnv_fuse_frame*, bnv_exchange_push; bnv_exchange_join before reading
- *   the map.  Only an event record / wait touches the fusing stream; routing and upsert run on a side stream. */
+/* Peer-memory variant of the exchange (csrc/bnv_p2p.cu): the sender routes each boundary record straight into the
+ * inbox of the ranks that need it (stores over NVLink into cudaIpc-mapped memory), the receiver upserts its inbox on a
+ * side stream once every peer's epoch sequence number has arrived -- no collective, no all-to-all traffic.  Usage, one
+ * process per GPU: bnv_map_set_shard, bnv_map_halo_enable, bnv_exchange_create, bnv_exchange_handle (64 bytes),
+ * all-gather the handles by any transport, bnv_exchange_connect; then bnv_exchange_push on every rank at the same
+ * points of the frame stream (pack + route + upsert of one epoch); bnv_exchange_join before reading the map.  Only the
+ * pack kernel and one event record / wait touch the fusing stream; routing and upsert run on a side stream. */
 typedef struct bnv_exchange bnv_exchange_t;
 int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_records_per_peer);
 int bnv_exchange_handle(bnv_exchange_t* ex, void* handle64_out_host);
 int bnv_exchange_connect(bnv_exchange_t* ex, const void* handles_host /* [world][64], rank order */);
-int bnv_exchange_begin_frame(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_push(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_join(bnv_exchange_t* ex, void* stream);
 int bnv_exchange_destroy(bnv_exchange_t* ex);

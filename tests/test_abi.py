@@ -43,7 +43,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     # host-buffer call and the experimental exchange validate their arguments before touching CUDA
     assert lib.bnv_fuse_frame_host(None, None, 480, 640, None, None, 3.0, None, 8, 1, None, None, None) == -1
     assert lib.bnv_exchange_create(ctypes.byref(h), None, 1024) == -1
-    assert lib.bnv_exchange_begin_frame(None, None) == -1
+    assert lib.bnv_map_halo_enable(None, 16) == -1 and lib.bnv_map_halo_pack(None, None, 16, None) == -1
     assert lib.bnv_exchange_push(None, None) == -1 and lib.bnv_exchange_join(None, None) == -1
     assert lib.bnv_exchange_destroy(None) == 0
 

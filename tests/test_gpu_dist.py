@@ -1,6 +1,6 @@
 """GPU (>= 2 B200s, NCCL): the tile shard through libbnv_b200 -- every rank fuses the same depth
 stream, keeps the rows of the voxels it owns, and exchanges boundary voxels with ONE all-gather per
-frame.  Union of the owned voxels must equal the single-GPU map bit for bit; every rank must decode
+exchange epoch (here every 3 frames of 4, so both the periodic epoch and the flush-on-read are exercised).  Union of the owned voxels must equal the single-GPU map bit for bit; every rank must decode
 the queries of its own tile exactly like the single-GPU map does."""
 import os
 import sys
@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
     model = _setup(dev)
     spec = synth.stream_spec("lounge")
     vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
-    shard = TileShardedFusion(vol, model, rank, world, brick_log2=4, exchange=exchange)
+    shard = TileShardedFusion(vol, model, rank, world, brick_log2=4, exchange=exchange, exchange_every=3)
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     rows = 0
     for fi in range(N_FRAMES):
@@ -62,7 +62,7 @@ def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
     dist.destroy_process_group()
 
 
-EXCHANGES = ["nccl"] + (["p2p"] if os.environ.get("BNV_TEST_P2P") == "1" else [])   # p2p: opt-in until validated
+EXCHANGES = ["nccl", "p2p"]
 
 
 @pytest.mark.parametrize("exchange", EXCHANGES)

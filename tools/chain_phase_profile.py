@@ -27,17 +27,39 @@ A = vol.active_coordinates.shape[0]
 off = torch.tensor([[a, b, c] for a in (-.5, 0, .5) for b in (-.5, 0, .5) for c in (-.5, 0, .5)], device="cuda")
 qc = (vol.active_coordinates.float()[:, None, :] + off[None]).reshape(1, A, 27, 3).contiguous()
 out = (C.c_ulonglong * 16)()
+names = ["wait L0", "epilogue+issue L1", "shadow1", "wait L1", "epilogue+issue L2", "shadow2",
+         "wait L2", "epilogue 3", "finish (issue L3 + next L0)"]
+
+
+def report(title, extra):
+    items = max(out[11], 1)
+    print("==", title)
+    tot = 0.0
+    for i, n in enumerate(names):
+        print(f"{n:32s} {out[i] / items:8.1f} cyc / item")
+        tot += out[i] / items
+    print(f"{'sum of phases':32s} {tot:8.1f} cyc / item")
+    print(f"{'per-tile precompute':32s} {out[9] / items:8.1f} cyc / item (amortised over the 8 corners)")
+    print(f"{'chain lifetime':32s} {out[10] / items:8.1f} cyc / item; {items} items timed; {extra}")
+
+
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 vol.decode_pts(qc, m.nerf, None, is_coords=True)
 prof(out, 1)                                   # discard warm-up (and the encode kernel's counts)
-vol.decode_pts(qc, m.nerf, None, is_coords=True)
-prof(out, 1)
-items = max(out[11], 1)
-names = ["wait L0", "epilogue+issue L1", "shadow1 (gather, blend prev)", "wait L1", "epilogue+issue L2", "shadow2 (stage next)",
-         "wait L2", "epilogue 3", "finish (issue L3 + next L0)"]
-tot = 0.0
-for i, n in enumerate(names):
-    print(f"{n:32s} {out[i] / items:8.1f} cyc / corner")
-    tot += out[i] / items
-print(f"{'sum of phases':32s} {tot:8.1f} cyc / corner")
-print(f"{'per-query precompute':32s} {out[9] / items:8.1f} cyc / corner (amortised over 8)")
-print(f"{'chain lifetime':32s} {out[10] / items:8.1f} cyc / corner; {A * 27} queries, {items} items timed")
+for cold in (False, True):
+    if cold:
+        flush.zero_()
+    vol.decode_pts(qc, m.nerf, None, is_coords=True)
+    prof(out, 1)
+    report("decode_tc_kernel, " + ("L2 flushed" if cold else "warm L2") + " (shadow1 = gather next + blend previous, shadow2 = stage next)",
+           f"{A * 27} queries")
+# the encode chain kernel (shadow1 = drain previous output + reductions, shadow2 = stage next corner)
+for cold in (False, True):
+    d, K, T = synth.make_frame(spec, 9, seed=0)
+    dd = torch.from_numpy(d.view(np.int16)).cuda().view(torch.uint16)
+    torch.cuda.synchronize(); prof(out, 1)
+    if cold:
+        flush.zero_()
+    m.fuse_depth_frame(vol, dd, K, T, spec.max_depth)
+    prof(out, 1)
+    report("encode_chain_kernel, " + ("L2 flushed" if cold else "warm L2"), "one 640x480 frame")

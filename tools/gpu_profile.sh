@@ -1,10 +1,12 @@
 #!/bin/bash
 # one gpurun call: launch list of the bench command + ncu --set full of the hot kernels (B200_PROFILING.md recipe)
+#   usage: tools/gpu_profile.sh <tag> [kernel-regex]
 mkdir -p gpurun_out
-TAG=${1:-r1b}
+TAG=${1:-r2a}
+KERN=${2:-'frame_prepass|encode_chain|finalize_fused|decode_tc|gtable_tc|blend_blocks|tsdf_integrate'}
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on \
-    -k regex:'encode_tc|finalize_fused|decode_tc|gtable_tc|blend_blocks|tsdf_integrate' --launch-skip 8 -c 10 -f \
+    -k regex:"$KERN" --launch-skip 12 -c 10 -f \
     -o gpurun_out/${TAG}_hot python tools/profile_workload.py > gpurun_out/${TAG}_hot.log 2>&1; echo "ncu full rc=$?"
 tail -2 gpurun_out/${TAG}_hot.log
