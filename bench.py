@@ -324,28 +324,39 @@ def run_b200(args):
     for i in range(args.warmup):
         step(i)
     barrier()
-    # ---- device-resident, L2 flushed between steps; per-kernel events for the roofline ---------
-    lib.bnv_map_set_timing(vol._handle, 1)
+    # ---- THE timed region: K steps, frames resident in HBM, L2 flushed between steps, one CUDA-event pair per step ----
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.bnv_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    enc_ms, fin_ms, pre_ms, rows_total, touched_total, kept_total = [], [], [], 0, 0, 0
     barrier()
     for i in range(args.steps):
         flush.zero_()
         ev[i][0].record()
         step(args.warmup + i)
         ev[i][1].record()
+    barrier()
+    launches = lib.bnv_launch_count() - launches0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    # ---- the same K cold steps again with CUDA events around every kernel (roofline): the three extra event records
+    # per step serialise the kernels' launch overlap and cost ~15 % of a 0.1 ms step, so they stay out of `value` ----
+    lib.bnv_map_set_timing(vol._handle, 1)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    enc_ms, fin_ms, pre_ms, rows_total, touched_total, kept_total = [], [], [], 0, 0, 0
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        ev2[i][0].record()
+        step(args.warmup + i)
+        ev2[i][1].record()
         ms3 = (C.c_float * 3)()
         _lib.check(lib.bnv_map_get_timing_stages(vol._handle, ms3), "timing")
         pre_ms.append(ms3[0]); enc_ms.append(ms3[1]); fin_ms.append(ms3[2])
         st = stats.tolist()
         rows_total += int(st[1]); touched_total += int(st[2]); kept_total += int(st[3])
     barrier()
-    launches = lib.bnv_launch_count() - launches0
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     lib.bnv_map_set_timing(vol._handle, 0)
+    staged_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev2]))
     # ---- same steps back to back (warm L2), one event pair ------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -459,7 +470,7 @@ def run_b200(args):
         dist.all_reduce(t)
         n_q_job, dec_ms_job = float(t[0]), maxr(dec_ms)
     ms = maxr(float(np.sum(step_ms))) / args.steps
-    warm_ms, e2e_ms, local_ms = maxr(warm_ms), maxr(e2e_ms), maxr(local_ms)
+    warm_ms, e2e_ms, local_ms, staged_ms = maxr(warm_ms), maxr(e2e_ms), maxr(local_ms), maxr(staged_ms)
     enc_avg = float(np.mean(enc_ms))
     rows_per_launch = rows_total / args.steps
     enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
@@ -483,6 +494,7 @@ def run_b200(args):
                        (f"one all-gather of boundary voxels per {args.exchange_every} frames" if args.exchange == "nccl"
                         else f"peer-memory boundary routing every {args.exchange_every} frames")},
             "value_warm": 1e3 / warm_ms,
+            "ms_per_step_with_kernel_events": staged_ms,
             "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
                     "d2h_bytes_per_step": 32,
                     "what": "bnv_fuse_frame_host per frame: pinned uint16 depth -> H2D (the next frame's copy is hinted and "
@@ -500,7 +512,9 @@ def run_b200(args):
                          "frac": enc_tflops / pk["tf_burst"],
                          "traffic": traffic("encode_chain_kernel" if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
                          "peak_source": pk["src"],
-                         "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "prepass_ms": pre_avg, "finalize_ms": fin_avg},
+                         "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "prepass_ms": pre_avg, "finalize_ms": fin_avg,
+                         "timing": "CUDA events around every kernel over a second pass of the same K cold steps "
+                                   "(ms_per_step_with_kernel_events); each event-bracketed kernel reads ~3-5 us long"},
             # the scatter stage is "HBM-bound by contract": the prepass (depth in, claims + counts, point
             # records out) and finalize (scratch rows in, map upsert) kernels carry all of the frame's algorithmic bytes
             "roofline_hbm": {"kernel": "frame_prepass_kernel + finalize_fused_kernel (scatter / upsert stage)", "bound": "hbm",

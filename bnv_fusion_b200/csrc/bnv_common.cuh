@@ -131,7 +131,6 @@ struct bnv_map {
   size_t prefetched_bytes;
   int stage_next;
   int64_t* user_stats;   // device int64[4] frame statistics of bnv_fuse_frame_host
-  double* zlut;         // [65536] (double)d / 1000.0 for every uint16 millimetre depth (load_depth, common.py:93)
   float* bp_pts;
   int32_t* bp_flags;
   int32_t* bp_scan;

@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t claim_none(int2 (&pr)[8]) {
 template <bool FROM_DEPTH>
 __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
   // dbg (tools/prepass_ablation.py only; 0 in production): 1 no claim atomics, 2 no global counter atomics,
-  // 4 no back-projection (every pixel invalid), 8 no record / key stores
+  // 4 no back-projection (every pixel invalid), 8 no record / key stores, 16 no depth staging
   __shared__ FrameTile tile;
   __shared__ int2 s_runs[kPreThreads / 32][256];       // per warp: (voxel key, run length) of up to 8 x 32 runs
   __shared__ int s_new[kPreThreads / 32], s_keep[kPreThreads / 32], s_stat[3], s_base[2];
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
   if (FROM_DEPTH) {
     const int tiles_x = (src.cam.W + kTileW - 1) / kTileW;
     const int u0 = (blockIdx.x % tiles_x) * kTileW, v0 = (blockIdx.x / tiles_x) * kTileH;
-    stage_frame_tile(tile, src.depth, src.cam, src.zlut, u0, v0);
+    if (!(dbg & 16)) stage_frame_tile(tile, src.depth, src.cam, u0, v0);     // reads the depth image only
     __syncthreads();
+    grid_dependency_wait();                                                  // the previous frame's finalize
     const int u = u0 + lane, v = v0 + warp;
     pix = v * src.cam.W + u;
     if (u < src.cam.W && v < src.cam.H && !(dbg & 4)) valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
       for (int j = 0; j < 6; ++j) p[j] = __ldg(src.pts6 + idx * 6 + j);
     }
     __syncthreads();
+    grid_dependency_wait();
   }
   // rule A1 (local_point_fusion.py:94-100): strict bounds one voxel inside the volume
   bool inb = valid;
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_rows_simt_kernel(MapDev m,
   float* sW = smem;
   float* sH = smem + EncMlp::kFloats + threadIdx.x;
   load_weights(sW, gW, EncMlp::kFloats);
+  grid_dependency_wait();                               // the prepass
   const int n_rec = m.ctr[4];
   const GeomDev& g = m.g;
   for (int64_t idx = (int64_t)blockIdx.x * kEncThreads + threadIdx.x; idx < n_rec; idx += (int64_t)gridDim.x * kEncThreads) {
@@ -302,6 +305,7 @@ __device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new
 __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_pts, bool f32acc, long long* __restrict__ stats,
                                                              long long* __restrict__ user_stats,
                                                              float* __restrict__ user_navg) {
+  grid_dependency_wait();                               // the encoder MLP kernel
   const int n_touched = m.ctr[1];
   int integrated = 0;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_touched; t += (int64_t)gridDim.x * blockDim.x) {
@@ -530,6 +534,22 @@ const float* bnv_internal_simt_weights(const bnv_mlp_t* mlp);
 int bnv_internal_encode_tc(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
 
 namespace bnv {
+// launch with programmatic stream serialization (see grid_dependency_wait in bnv_frame.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static int g_prepass_debug = 0;      // profiling ablations only (bnv_debug_prepass, not part of the ABI header)
 // kernels 1 + 2 of the frame: prepass over `n_threads` pixels / points, then the encoder MLP over the records
 static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int64_t n_threads,
@@ -543,10 +563,11 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
   if (n_threads == 0) return BNV_OK;
   if (from_depth) {
     const unsigned tiles = (unsigned)(((src.cam.W + kTileW - 1) / kTileW) * ((src.cam.H + kTileH - 1) / kTileH));
-    frame_prepass_kernel<true><<<tiles, kPreThreads, 0, s>>>(map->d, src, (long long*)map->stats, g_prepass_debug);
+    BNV_CUDA(launch_pdl(frame_prepass_kernel<true>, dim3(tiles), dim3(kPreThreads), 0, s, map->d, src, (long long*)map->stats,
+                        g_prepass_debug));
   } else {
-    frame_prepass_kernel<false><<<(unsigned)((n_threads + kPreThreads - 1) / kPreThreads), kPreThreads, 0, s>>>(
-        map->d, src, (long long*)map->stats, g_prepass_debug);
+    BNV_CUDA(launch_pdl(frame_prepass_kernel<false>, dim3((unsigned)((n_threads + kPreThreads - 1) / kPreThreads)),
+                        dim3(kPreThreads), 0, s, map->d, src, (long long*)map->stats, g_prepass_debug));
   }
   BNV_LAUNCH_CHECK("frame_prepass_kernel");
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[3], s));
@@ -557,14 +578,15 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
     attr[map->device & 63] = true;
   }
   const int64_t blocks = (n_threads + kEncThreads - 1) / kEncThreads;
-  encode_rows_simt_kernel<<<(unsigned)(blocks < 148 * 2 ? blocks : 148 * 2), kEncThreads, kEncSmem, s>>>(
-      map->d, bnv_internal_simt_weights(enc));
+  BNV_CUDA(launch_pdl(encode_rows_simt_kernel, dim3((unsigned)(blocks < 148 * 2 ? blocks : 148 * 2)), dim3(kEncThreads),
+                      kEncSmem, s, map->d, bnv_internal_simt_weights(enc)));
   BNV_LAUNCH_CHECK("encode_rows_simt_kernel");
   return BNV_OK;
 }
 
 static int launch_finalize(bnv_map_t* map, int min_pts, int mode, int64_t* frame_stats, float* navg, cudaStream_t s) {
-  finalize_fused_kernel<<<148 * 4, 256, 0, s>>>(map->d, min_pts, mode == BNV_MLP_TC16, (long long*)map->stats, (long long*)frame_stats, navg);
+  BNV_CUDA(launch_pdl(finalize_fused_kernel, dim3(148 * 4), dim3(256), 0, s, map->d, min_pts, mode == BNV_MLP_TC16,
+                      (long long*)map->stats, (long long*)frame_stats, navg));
   BNV_LAUNCH_CHECK("finalize_fused_kernel");
   return BNV_OK;
 }
@@ -602,7 +624,6 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   int rc = make_camera(src.cam, H, W, K, T, max_depth);
   if (rc) return rc;
   src.depth = depth;
-  src.zlut = map->zlut;
   cudaStream_t s = (cudaStream_t)stream;
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
   rc = launch_encode(map, src, true, (int64_t)H * W, enc, mode, s);

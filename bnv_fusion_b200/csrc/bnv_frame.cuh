@@ -94,7 +94,6 @@ __device__ __forceinline__ bool backproject_pixel(const uint16_t* __restrict__ d
 // (u - cx) / fx, (v - cy) / fy of the apron's (clamped) columns / rows in shared memory.  Bit-identical to
 // backproject_pixel: every quotient and every masked depth is produced by the same correctly-rounded operations,
 // only once per tile instead of once per use (30 float64 divisions per pixel -> 3).
-//   zlut[d] = (double)d / 1000.0 for every uint16 depth value (device table, built at map creation)
 constexpr int kTileW = 32, kTileH = 8;
 struct FrameTile {
   double z[kTileH + 2][kTileW + 2];
@@ -103,12 +102,14 @@ struct FrameTile {
 };
 
 __device__ __forceinline__ void stage_frame_tile(FrameTile& t, const uint16_t* __restrict__ depth, const Camera& cam,
-                                                 const double* __restrict__ zlut, int u0, int v0) {
+                                                 int u0, int v0) {
   const double fx = (double)cam.fx, fy = (double)cam.fy, cx = (double)cam.cx, cy = (double)cam.cy;
   for (int i = threadIdx.x; i < (kTileH + 2) * (kTileW + 2); i += blockDim.x) {
     const int yy = i / (kTileW + 2), xx = i - yy * (kTileW + 2);
     const int uu = min(max(u0 - 1 + xx, 0), cam.W - 1), vv = min(max(v0 - 1 + yy, 0), cam.H - 1);
-    const double z = __ldg(zlut + __ldg(depth + (size_t)vv * cam.W + uu));
+    // load_depth (src/utils/common.py:93): uint16 millimetres / 1000. in float64 -- one correctly rounded division
+    // per staged pixel (a lookup table would cost a second dependent memory round trip per tile)
+    const double z = __ddiv_rn((double)__ldg(depth + (size_t)vv * cam.W + uu), 1000.0);
     t.z[yy][xx] = (z > 0.0 && z < cam.max_depth) ? z : 0.0;
   }
   if (threadIdx.x < kTileW + 2) {
@@ -144,8 +145,12 @@ struct EncSrc {
   Camera cam;
   const float* pts6;       // !FROM_DEPTH
   int64_t n_points;
-  const double* zlut;      // FROM_DEPTH: millimetres -> metres table (bnv_map::zlut)
 };
+
+// Programmatic dependent launch (sm_90+): the frame's kernels are launched with programmatic stream serialization,
+// so a kernel's launch and prologue overlap the tail of the kernel before it; everything that depends on that
+// kernel's results comes after this wait (a no-op for a normally launched kernel).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- per-frame scratch (MapDev::ftable / fkeys / fsum) ------------------------------------------------
 __device__ __forceinline__ int32_t ft_count(unsigned long long e) { return (int32_t)(e & 0xffffffffull); }

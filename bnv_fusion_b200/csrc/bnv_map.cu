@@ -160,12 +160,6 @@ __global__ void count_optim_apply_kernel(int32_t* __restrict__ flags, float* __r
   }
 }
 
-// millimetre depth -> metric depth exactly as load_depth computes it (float64 division, src/utils/common.py:93)
-__global__ void zlut_kernel(double* __restrict__ z) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 65536) z[i] = __ddiv_rn((double)i, 1000.0);
-}
-
 // boundary exchange, sender side: one record {flat id, weight, feat[8]} with the CURRENT values of every shell voxel
 // integrated since the last exchange (the dirty list holds each such slot once), flags cleared on the way
 __global__ void __launch_bounds__(256) halo_pack_kernel(MapDev m, int32_t* __restrict__ buf, int cap) {
@@ -329,7 +323,6 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   alloc((void**)&m->sort_vals_out, (size_t)d.fcap * 4);
   alloc((void**)&m->flags, (size_t)aux * 4);
   alloc((void**)&m->scan, (size_t)aux * 4);
-  alloc((void**)&m->zlut, 65536 * sizeof(double));
   alloc((void**)&m->depth_stage[0], (size_t)max_points * 2);
   alloc((void**)&m->depth_stage[1], (size_t)max_points * 2);
   alloc((void**)&m->user_stats, 4 * 8);
@@ -354,8 +347,6 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   BNV_CUDA(cudaMemsetAsync(m->flags, 0, (size_t)aux * 4, 0));
   BNV_CUDA(cudaMemsetAsync(m->stats, 0, 64, 0));
   BNV_CUDA(cudaMemsetAsync(d.ftable, 0, (size_t)g.n_vox * 8, 0));
-  zlut_kernel<<<256, 256>>>(m->zlut);
-  BNV_LAUNCH_CHECK("zlut_kernel");
   BNV_CUDA(cudaStreamSynchronize(0));
   return BNV_OK;
 }
@@ -366,7 +357,7 @@ int bnv_map_destroy(bnv_map_t* m) {
   MapDev& d = m->d;
   void* ptrs[] = {d.table, d.ftable, d.keys, d.feats, d.weights, d.hits, d.fkeys, d.fsum, d.prec, d.ftable_dummy, d.dirty_flag, d.dirty_list,
                   d.ctr, m->sort_keys_in, m->sort_keys_out, m->sort_vals_in,
-                  m->sort_vals_out, m->flags, m->scan, m->zlut, m->depth_stage[0], m->depth_stage[1], m->user_stats, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
+                  m->sort_vals_out, m->flags, m->scan, m->depth_stage[0], m->depth_stage[1], m->user_stats, m->bp_pts, m->bp_flags, m->bp_scan, m->stats, m->dec_pack, m->gtable,
                   m->cub_tmp};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]);

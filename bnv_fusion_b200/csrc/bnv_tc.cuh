@@ -291,6 +291,7 @@ template <int NWG>
 struct TcShared {
   uint64_t bar_d[NWG];
   uint64_t bar_o[NWG];
+  uint64_t bar_w;                // weight image arrived (cp.async.bulk complete_tx)
   uint32_t tmem_base;
   uint32_t live[NWG][2][4];      // per-warp corner masks of the tile shard (double-buffered)
 };
@@ -298,22 +299,27 @@ struct TcShared {
 template <int NWG>
 __device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
                                                int w_bytes) {
-  const int tid = threadIdx.x, warp = tid >> 5, wg = tid >> 7;
-  for (int i = tid * 16; i < w_bytes; i += blockDim.x * 16)
-    *reinterpret_cast<uint4*>(s_weights + i) = __ldg(reinterpret_cast<const uint4*>(g_weights + i));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // weight image -> shared memory with ONE bulk async copy (TMA engine, cp.async.bulk: no registers, no per-thread
+  // loads) that signals an mbarrier with its byte count; barrier init and TMEM allocation overlap the transfer
   if (tid == 0) {
 #pragma unroll
     for (int g = 0; g < NWG; ++g) {
       mbar_init(&sh.bar_d[g], 1);
       mbar_init(&sh.bar_o[g], 1);
     }
+    mbar_init(&sh.bar_w, 1);
     mbar_fence_init();
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sh.bar_w)), "r"((uint32_t)w_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(s_weights)), "l"(g_weights), "r"((uint32_t)w_bytes), "r"(smem_u32(&sh.bar_w))
+                 : "memory");
   }
   if (warp == 0) tmem_alloc(&sh.tmem_base, 512);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(&sh.bar_w, 0);                 // the weights have landed (async proxy writes, made visible by the mbarrier)
   RowChain c;
   // warp-uniform values are broadcast with shfl so that the compiler can keep them in uniform registers
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0), wg_u = warp_u >> 2;

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
   RowChain c = tc_setup<kNWG>(S.sh, weights_smem<SmemEnc>(smem), gW, w_bytes);
   const int wg = threadIdx.x >> 7, r = threadIdx.x & 127, warp_in_wg = r >> 5, tid = threadIdx.x;
   const GeomDev& g = m.g;
+  grid_dependency_wait();                               // the prepass (setup above overlapped its tail)
   const int64_t n_rec = m.ctr[4];                       // point records written by frame_prepass_kernel
   const int64_t n_units = ((n_rec + 127) / 128) * 8;
   const int64_t chain = (int64_t)blockIdx.x * kNWG + wg, n_chains = (int64_t)gridDim.x * kNWG;
@@ -273,31 +274,21 @@ __global__ void __launch_bounds__(kThreads, 1) encode_chain_kernel(MapDev m, con
 }
 
 // ---- fused decode -----------------------------------------------------------------------------------
+// (A variant that prefetched the table entries and feature rows ONE TILE ahead with cp.async into shared memory was
+// measured in round 2: 5.6 instead of 6.1 Gqueries/s -- the chain is bound by the instructions each warp issues per
+// corner, not by the gather latency, and the extra shared-memory traffic costs more than the exposed latency saved.)
 // Per-query state lives in shared memory ([word][thread], conflict-free, thread-private): everything that
 // depends on one axis only exists in a floor (s = 0) and a ceil (s = 1) flavour computed once per query,
 // a corner row is then 4 gathered words + 6 selected words + 6 constants.  Keeping it out of the register
 // file leaves room for the 96 transient registers of the hidden-layer epilogue (no spills) and lets the
 // 8-corner loop stay rolled (8x less code, no instruction-cache misses).
-//
-// Latency: a query needs two dependent scattered reads per corner (table entry -> packed feature row) that
-// hit L2 at best.  They are software-pipelined ONE TILE AHEAD with cp.async (global -> shared memory without
-// registers, zero-fill for misses): while tile i runs its 8 corners through the chain, the table entries of tile
-// i + 1 are fetched during corner 1, its feature rows and weights during corner 7 (by then every staging slot of
-// tile i has been consumed), its per-axis words are computed in the shadow of the last layer of corner 7.  The
-// chain never waits for a gather (profiles/r2a: the one-corner-ahead register prefetch left 900 of 3500 cycles per
-// corner exposed in the staging shadow and 1800 per corner in the per-tile precompute).
 struct DecState {
   uint32_t w_ls[3][2][kThreads];   // fp16x2 {l, sin l}
   uint32_t w_c1[3][2][kThreads];   // fp16x2 {cos l, 1}
   float t[3][2][kThreads];         // 1 - |l|
   int32_t ts[3][2][kThreads];      // TSDF-prior index * its stride, or INT_MIN when outside (nearest lookup)
-  uint4 feat[8][kThreads];         // packed fp16x8 feature row of corner k (zeros on a miss), cp.async target
-  float wt[8][kThreads];           // fusion weight of corner k (0 on a miss), cp.async target
-  int32_t slot[8][kThreads];       // table entry of corner k of the NEXT tile (_query_tensor), cp.async target
-  float nq[3][kThreads];           // voxel-unit coordinates of the NEXT tile's query
+  int32_t slot[8][kThreads];       // table lookup of corner k (_query_tensor)
 };
-
-__device__ const int32_t g_kempty_word = kEmpty;   // source of the table "lookup" of an out-of-grid corner
 
 __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArgs a, const uint4* __restrict__ packed,
                                                                  const uint8_t* __restrict__ gW, int w_bytes) {
@@ -307,7 +298,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
   DecState& Q = *reinterpret_cast<DecState*>(weights_smem<Smem>(smem) + ((w_bytes + 127) / 128) * 128);
   const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127;
   const int64_t n_tiles = (a.n_queries + 127) / 128;
-  const int64_t stride = (int64_t)gridDim.x * kNWG;
   const GeomDev& g = m.g;
   constexpr int32_t kOut = INT_MIN;
   const bool has_prior = a.tsdf != nullptr;
@@ -318,85 +308,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     const int32_t px = Q.ts[0][corner_sx(k)][tid], py = Q.ts[1][corner_sy(k)][tid], pz = Q.ts[2][corner_sz(k)][tid];
     return (px != kOut && py != kOut && pz != kOut) ? __ldg(a.tsdf + ((int64_t)px + py + pz)) : 0.f;
   };
-  auto stage_corner = [&](int k) {
+  auto gather = [&](int k, uint4& f, float& w) {                                         // D3
+    f = make_uint4(0, 0, 0, 0);
+    w = 0.f;
+    const int32_t s = Q.slot[k][tid];
+    if (s >= 0 && s < a.n_rows) {
+      f = __ldg(packed + s);
+      w = __ldg(a.weights_rows + s);
+    }
+  };
+  auto stage_corner = [&](int k, const uint4& f) {
     const int sx = corner_sx(k), sy = corner_sy(k), sz = corner_sz(k);
-    const uint4 f = Q.feat[k][tid];
     const uint32_t in[16] = {f.x, f.y, f.z, f.w,
                              Q.w_ls[0][sx][tid], Q.w_c1[0][sx][tid], Q.w_ls[1][sy][tid], Q.w_c1[1][sy][tid],
                              Q.w_ls[2][sz][tid], Q.w_c1[2][sz][tid], kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
     chain_stage<16>(c, in);
-  };
-  // query coordinates of tile `tile` -> Q.nq (zeros past the end)
-  auto load_coords = [&](int64_t tile) {
-    const int64_t q = tile * 128 + r;
-    float cq[3] = {0.f, 0.f, 0.f};
-    if (tile < n_tiles && q < a.n_queries) query_coords(m, a, q, cq);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) Q.nq[d][tid] = cq[d];
-  };
-  // the 8 table entries of the query in Q.nq -> Q.slot (D3, _query_tensor): 8 x 4-byte cp.async
-  auto fetch_slots = [&](bool live) {
-    int32_t tab[3][2];
-    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float cq = Q.nq[d][tid];
-      const float nbv[2] = {floorf(cq), ceilf(cq)};
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int iv = (int)nbv[s];
-        tab[d][s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int32_t tx = tab[0][corner_sx(k)], ty = tab[1][corner_sy(k)], tz = tab[2][corner_sz(k)];
-      const bool in_grid = tx != kOut && ty != kOut && tz != kOut;
-      const int32_t* src = in_grid ? m.table + ((int64_t)tx + ty + tz) : &g_kempty_word;
-      cp_async4(&Q.slot[k][tid], src);
-    }
-    cp_async_commit();
-  };
-  // feature rows + fusion weights of the 8 corners in Q.slot -> Q.feat / Q.wt (zeros on a miss)
-  auto fetch_rows = [&]() {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int32_t s = Q.slot[k][tid];
-      const bool hit = s >= 0 && s < a.n_rows;
-      cp_async16_zfill(&Q.feat[k][tid], packed + (hit ? s : 0), hit);
-      cp_async4_zfill(&Q.wt[k][tid], a.weights_rows + (hit ? s : 0), hit);
-    }
-    cp_async_commit();
-  };
-  // everything that depends on one axis only, for the query in Q.nq (D1, D2, D6)
-  auto axis_state = [&]() {
-    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const float cq = Q.nq[d][tid];
-      const float nbv[2] = {floorf(cq), ceilf(cq)};
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const float l = __fsub_rn(cq, nbv[s]);                                           // D1
-        float sn, cs;
-        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
-        Q.w_ls[d][s][tid] = pack_f16x2(l, sn);
-        Q.w_c1[d][s][tid] = pack_f16x2(cs, 1.0f);
-        Q.t[d][s][tid] = __fsub_rn(1.f, fabsf(l));
-        int32_t ts = kOut;
-        if (has_prior) {                                                                 // grid_sample(nearest), D6
-          float t = __fdiv_rn(nbv[s], a.nm1[d]);
-          t = __fmul_rn(t, 2.f);
-          t = __fsub_rn(t, 1.f);
-          t = __fadd_rn(t, 1.f);
-          t = __fmul_rn(t, 0.5f);
-          t = __fmul_rn(t, a.tm1[d]);
-          const float rr = nearbyintf(t);
-          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ts = (int)rr * pstride[d];
-        }
-        Q.ts[d][s][tid] = ts;
-      }
-    }
   };
   // the query whose last corner is still in D_out
   bool pending = false, p_live = false;
@@ -417,39 +343,80 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     }
   };
   BNV_PROF_MARK(p_life);
-  int64_t tile = (int64_t)blockIdx.x * kNWG + wg;
-  if (tile < n_tiles) {          // pipeline prologue: the first tile's lookups, synchronously
-    load_coords(tile);
-    fetch_slots(tile * 128 + r < a.n_queries);
-    axis_state();
-    cp_async_wait_all();
-    fetch_rows();
-  }
-  for (; tile < n_tiles; tile += stride) {
+  for (int64_t tile = (int64_t)blockIdx.x * kNWG + wg; tile < n_tiles; tile += (int64_t)gridDim.x * kNWG) {
     BNV_PROF_MARK(p_pre);
     const int64_t q = tile * 128 + r;
     const bool live = q < a.n_queries;
-    cp_async_wait_all();                      // this tile's feature rows / weights (issued a whole corner ago)
-    float wsum = 0.f, minw = 3.0e38f;
+    float cq[3] = {0.f, 0.f, 0.f};
+    if (live) query_coords(m, a, q, cq);
+    // ---- once per query: everything that depends on one axis only ---------------------------------
+    int32_t tab[3][2];                // voxel index * table stride of this axis, or INT_MIN when outside the grid
+    const int32_t tstride[3] = {g.nyz, g.n[2], 1};
+    const int32_t pstride[3] = {a.tsdf_dims[1] * a.tsdf_dims[2], a.tsdf_dims[2], 1};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float nbv[2] = {floorf(cq[d]), ceilf(cq[d])};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const float l = __fsub_rn(cq[d], nbv[s]);                                        // D1
+        float sn, cs;
+        __sincosf(l, &sn, &cs);                                                          // |l| <= 1
+        Q.w_ls[d][s][tid] = pack_f16x2(l, sn);
+        Q.w_c1[d][s][tid] = pack_f16x2(cs, 1.0f);
+        Q.t[d][s][tid] = __fsub_rn(1.f, fabsf(l));
+        const int iv = (int)nbv[s];
+        tab[d][s] = (live && iv >= 0 && iv < g.n[d]) ? iv * tstride[d] : kOut;
+        int32_t ts = kOut;
+        if (has_prior) {                                                                 // grid_sample(nearest), D6
+          float t = __fdiv_rn(nbv[s], a.nm1[d]);
+          t = __fmul_rn(t, 2.f);
+          t = __fsub_rn(t, 1.f);
+          t = __fadd_rn(t, 1.f);
+          t = __fmul_rn(t, 0.5f);
+          t = __fmul_rn(t, a.tm1[d]);
+          const float rr = nearbyintf(t);
+          if (rr >= 0.f && rr < (float)a.tsdf_dims[d]) ts = (int)rr * pstride[d];
+        }
+        Q.ts[d][s][tid] = ts;
+      }
+    }
+    float wsum = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float w = weight_of(k);
       wsum = k == 0 ? w : __fadd_rn(wsum, w);                                            // D2 normaliser
-      minw = fminf(minw, Q.wt[k][tid]);                                                  // D3
+    }
+    // ---- 8 independent table lookups in flight (_query_tensor, D3) ---------------------------------
+    int32_t slot0 = kEmpty;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int32_t tx = tab[0][corner_sx(k)], ty = tab[1][corner_sy(k)], tz = tab[2][corner_sz(k)];
+      int32_t sl = kEmpty;
+      if (tx != kOut && ty != kOut && tz != kOut) sl = __ldg(m.table + ((int64_t)tx + ty + tz));
+      Q.slot[k][tid] = sl;
+      if (k == 0) slot0 = sl;
+    }
+    uint4 f_nxt = make_uint4(0, 0, 0, 0);
+    float w_nxt = 0.f;
+    if (slot0 >= 0 && slot0 < a.n_rows) {
+      f_nxt = __ldg(packed + slot0);
+      w_nxt = __ldg(a.weights_rows + slot0);
     }
     // the previous query's last corner has been in flight during all of the above
     drain();
-    float sdf = 0.f, dsum = 0.f;
-    stage_corner(0);
+    float minw = 3.0e38f, sdf = 0.f, dsum = 0.f;
+    stage_corner(0, f_nxt);
     chain_begin<16>(c);
     BNV_PROF_ADD(9, p_pre);
-    const bool has_next_tile = tile + stride < n_tiles;
+    float w_cur = w_nxt;
 #pragma unroll 1
     for (int k = 0; k < 8; ++k) {
+      minw = fminf(minw, w_cur);                                                         // D3
       chain_hidden<16>(
           c,
           [&]() {
-            // shadow of the second layer: blend the previous corner; feed the next tile's pipeline
+            // shadow of the second layer: issue the next corner's gather, blend the previous corner
+            if (k < 7) gather(k + 1, f_nxt, w_nxt);
             if (k > 0) {
               float y[1];
               chain_output<1>(c, y);                                                    // D7: all 8 rows are evaluated
@@ -457,27 +424,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
               sdf = __fadd_rn(sdf, __fmul_rn(__fmul_rn(y[0], g.vs), wn));                // D4, D5
               if (has_prior) dsum = __fadd_rn(dsum, __fmul_rn(prior_of(k - 1), wn));     // D6
             }
-            if (k == 0) {
-              load_coords(tile + stride);
-            } else if (k == 1) {
-              fetch_slots(has_next_tile && (tile + stride) * 128 + r < a.n_queries);
-            } else if (k == 7) {
-              cp_async_wait_all();            // the next tile's table entries (issued six corners ago)
-              fetch_rows();                   // every staging slot of this tile has been consumed
-            }
           },
           [&]() {
-            // shadow of the third layer: stage the next corner's row; after the last staging the per-axis words
-            // are free for the next tile (corner 7's blend weight and prior are saved first)
-            if (k < 7) {
-              stage_corner(k + 1);
-            } else {
-              p_wn = __fdiv_rn(weight_of(7), wsum);
-              p_dl = has_prior ? prior_of(7) : 0.f;
-              axis_state();
-            }
+            // shadow of the third layer: the gather has landed -> stage the next corner's row
+            if (k < 7) stage_corner(k + 1, f_nxt);
           });
       chain_finish<16>(c, k < 7);
+      w_cur = w_nxt;
     }
     // corner 7 is in flight: finish this query at the top of the next tile (or after the loop)
     pending = true;
@@ -486,9 +439,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_tc_kernel(MapDev m, DecArg
     p_sdf = sdf;
     p_dsum = dsum;
     p_minw = minw;
+    p_wn = __fdiv_rn(weight_of(7), wsum);
+    p_dl = has_prior ? prior_of(7) : 0.f;
   }
   drain();
-  cp_async_wait_all();
   BNV_PROF_ADD(10, p_life);
   tc_teardown<kNWG>(S.sh);
 }
@@ -596,7 +550,19 @@ int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp
   int rc = set_smem(encode_chain_kernel, smem);
   if (rc) return rc;
   const int grid = grid_for(((max_records + 127) / 128) * 8);        // units = (tile, corner)
-  encode_chain_kernel<<<grid, kThreads, smem, s>>>(map->d, (const uint8_t*)enc->w16, (int)enc->w16_bytes);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     // see grid_dependency_wait (bnv_frame.cuh)
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BNV_CUDA(cudaLaunchKernelEx(&cfg, encode_chain_kernel, map->d, (const uint8_t*)enc->w16, (int)enc->w16_bytes));
+  }
   BNV_LAUNCH_CHECK("encode_chain_kernel");
   return BNV_OK;
 }

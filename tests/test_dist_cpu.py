@@ -1,5 +1,6 @@
-"""CPU, gloo, world_size 2 and 3: the tile-shard logic (ownership, one all-gather per frame of boundary
-records, halo selection) on top of the numpy oracle.  The union of the ranks' owned voxels must equal
+"""CPU, gloo, world_size 2 and 3: the tile-shard logic (ownership, one all-gather of boundary records per exchange
+EPOCH -- every EVERY frames and once more before the map is read, carrying the current values of every shell voxel
+integrated since the last epoch -- halo selection) on top of the numpy oracle.  The union of the ranks' owned voxels must equal
 the single-process map bit for bit, and every rank must hold the halo voxels its own queries need."""
 import os
 import sys
@@ -20,6 +21,7 @@ from bnv_fusion_b200 import synth          # noqa: E402
 BRICK = 2      # 4-voxel bricks so that the 32^3 test grid has several bricks per rank
 CAP = 4096
 N_FRAMES = 10
+EVERY = 4        # frames per exchange epoch: epochs after frames 4 and 8, flush after frame 10
 
 
 def _sharded_encode(pts6, grid, enc, rank, world):
@@ -50,6 +52,7 @@ def _worker(rank, world, port, out_dir):
     grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
     vm = O.VoxelMap(grid)
     nyz = grid.n_xyz[1] * grid.n_xyz[2]
+    dirty = set()
     for fi in range(N_FRAMES):
         d, K, T = synth.make_frame(spec, fi, seed=0)
         depth, mask = O.load_depth_u16(d, spec.max_depth)
@@ -58,18 +61,22 @@ def _worker(rank, world, port, out_dir):
         if res is not None:
             feats, cnt, flat = res
             O.integrate(vm, flat, feats, cnt)
-        # boundary records integrated this frame -> ONE all-gather -> upsert what this rank needs
-        b = flat[D.on_brick_shell(D.unflatten(flat, grid.n_xyz), BRICK)]
-        f, w, _, _ = vm.query(b)
-        mine = torch.from_numpy(D.pack_halo(b, w, f, CAP))
-        gathered = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        per_rank = D.unpack_gathered(torch.cat(gathered).numpy(), world, CAP)
-        for r, (hf, hw, hfeat) in enumerate(per_rank):
-            if r == rank:
-                continue
-            need = D.select_needed(hf, grid.n_xyz, rank, world, BRICK)
-            vm.insert(hf[need], hfeat[need], hw[need], np.zeros(int(need.sum()), np.float32))
+        # shell voxels integrated since the last epoch, each remembered once (bnv_map.cu: dirty flag + list)
+        dirty.update(flat[D.on_brick_shell(D.unflatten(flat, grid.n_xyz), BRICK)].tolist())
+        if (fi + 1) % EVERY == 0 or fi == N_FRAMES - 1:
+            # one epoch: records with the CURRENT values -> ONE all-gather -> upsert what this rank needs
+            b = np.fromiter(sorted(dirty), dtype=np.int64, count=len(dirty))
+            dirty.clear()
+            f, w, _, _ = vm.query(b)
+            mine = torch.from_numpy(D.pack_halo(b, w, f, CAP))
+            gathered = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            per_rank = D.unpack_gathered(torch.cat(gathered).numpy(), world, CAP)
+            for r, (hf, hw, hfeat) in enumerate(per_rank):
+                if r == rank:
+                    continue
+                need = D.select_needed(hf, grid.n_xyz, rank, world, BRICK)
+                vm.insert(hf[need], hfeat[need], hw[need], np.zeros(int(need.sum()), np.float32))
     keys = np.fromiter(vm.index.keys(), dtype=np.int64)
     f, w, _, _ = vm.query(keys)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), keys=keys, feats=f, weights=w)

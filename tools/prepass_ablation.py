@@ -1,5 +1,5 @@
 """Ablation of the frame prepass kernel (profiling aid): bnv_debug_prepass flags 1 no claim atomics, 2 no global counter
-atomics, 4 no back-projection, 8 no record stores; prints the three stage times (prepass / MLP / finalize) of a lounge
+atomics, 4 no back-projection, 8 no record stores, 16 no depth staging; prints the three stage times (prepass / MLP / finalize) of a lounge
 frame, L2 flushed.  The map is garbage after a run with flags != 0 -- each configuration uses a fresh volume."""
 import os, sys, ctypes as C
 import numpy as np, torch
@@ -19,7 +19,7 @@ spec = synth.stream_spec("lounge")
 frames = [synth.make_frame(spec, i, seed=0) for i in range(4)]
 dd = [torch.from_numpy(d.view(np.int16)).cuda().view(torch.uint16) for d, _, _ in frames]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for flags in [int(a) for a in (sys.argv[1:] or ["0", "1", "2", "3", "4", "8", "15"])]:
+for flags in [int(a) for a in (sys.argv[1:] or ["0", "1", "3", "4", "16", "31"])]:
     vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8)
     lib.bnv_map_set_timing(vol._handle, 1)
     lib.bnv_debug_prepass(flags)
