@@ -58,17 +58,19 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons during the timed region.  nvidia-smi needs a few hundred milliseconds to
+    deliver its first sample (longer with 8 ranks starting one each), so the sampler is started early and `mark()`ed
+    where the timed region begins; the report covers the samples after the mark."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark = [], None, index, 0.0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,23 +79,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t >= self.t_mark and len(r) >= 6]
+        scope = "timed region .. end of the e2e loop"
+        if not rows:
+            rows, scope = [r for _, r in self.rows if len(r) >= 6], "whole run (no sample fell inside the timed region)"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 def make_frames(n):
@@ -274,6 +283,8 @@ def run_b200(args):
         config.set_mlp_mode(args.mlp)
     lib = _lib.load()
     pk = peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
 
     spec, frames = make_frames(N_FRAMES)
     p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
@@ -325,8 +336,7 @@ def run_b200(args):
         step(i)
     barrier()
     # ---- THE timed region: K steps, frames resident in HBM, L2 flushed between steps, one CUDA-event pair per step ----
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     launches0 = lib.bnv_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -644,6 +654,92 @@ def run_paced(args):
         dist.destroy_process_group()
 
 
+def run_sustained(args):
+    """BASELINE.json configs[2]: a long 640x480 stream (default 1000 frames) through the host-buffer call, unpaced: every
+    frame is H2D-copied from pinned memory, fused, and its statistics read back before the next one.  64 distinct
+    synthetic frames on a smooth orbit are cycled (the map keeps growing for the first cycle, then revisits).  Opt-in
+    (`--sustained 1000`); prints its own JSON line: sustained frames/s over the whole run, per-100-frame rates (drift),
+    clocks during the run, final map size.  Tile-sharded when launched on N > 1 GPUs."""
+    import torch
+    import torch.distributed as dist
+    from bnv_fusion_b200 import config, synth
+    from bnv_fusion_b200.model import LitFusionPointNet
+    from bnv_fusion_b200.volume import SparseVolume
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if args.mlp:
+        config.set_mlp_mode(args.mlp)
+    sampler = ClockSampler(local)
+    sampler.start()
+    spec = synth.stream_spec(WORKLOAD)
+    n_src = 64
+    frames = [synth.make_frame(spec, i, seed=0) for i in range(n_src)]
+    p = np.load(os.path.join(ROOT, "tests", "golden", "tcnn_params.npz"))
+    cfg = {"trainer": {"dense_volume": False},
+           "model": {"feature_vector_size": 8, "voxel_size": spec.voxel_size, "min_pts_in_grid": 8,
+                     "point_net": {"in_channels": 6}, "nerf": {"num_encoding_fn_xyz": 1}}}
+    model = LitFusionPointNet(cfg)
+    model.load_state_dict({"pointnet_backbone.model.params": torch.from_numpy(p["encoder"]),
+                           "nerf.model.params": torch.from_numpy(p["decoder"])})
+    model.eval(); model.cuda(); model.freeze()
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    target, pre = model, (vol,)
+    if world > 1:
+        from bnv_fusion_b200.dist import TileShardedFusion
+        target, pre = TileShardedFusion(vol, model, rank, world, brick_log2=args.brick_log2, exchange=args.exchange,
+                                        exchange_every=args.exchange_every), ()
+    host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
+    stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+    def one(i):
+        _, K, T = frames[i % n_src]
+        target.fuse_depth_frame_host(*pre, host[i % n_src], K, T, spec.max_depth, stats_host=stats_host,
+                                     next_depth_mm_host=host[(i + 1) % n_src])
+        torch.cuda.current_stream().synchronize()
+
+    for i in range(max(args.warmup, 5)):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = int(args.sustained)
+    sampler.mark()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n // 100 + 1)]
+    marks[0].record()
+    for i in range(n):
+        one(i)
+        if (i + 1) % 100 == 0:
+            marks[(i + 1) // 100].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    vol.check_status()
+    seg = [marks[j].elapsed_time(marks[j + 1]) for j in range(n // 100)]
+    total_ms = float(np.sum(seg))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    n_vox = len(vol)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "sustained_fusion_frames_per_sec", "value": (n // 100) * 100 / (total_ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": (n // 100) * 100, "warmup": max(args.warmup, 5), "higher_is_better": True, "data": "synthetic",
+            "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
+            "config": {"workload": WORKLOAD_DESC + f"; {n_src} distinct frames cycled, host buffers (H2D + stats D2H every frame)",
+                       "parallelism": "1 GPU" if world == 1 else f"tile shard over {world} GPUs ({args.exchange} exchange every {args.exchange_every} frames)"},
+            "frames_per_sec_per_100_frames": [100.0 / (m * 1e-3) for m in seg],
+            "clocks": clocks, "map_voxels_rank0": n_vox,
+            "e2e": {"value": (n // 100) * 100 / (total_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": spec.height * spec.width * 2 + 100,
+                    "d2h_bytes_per_step": 32}}))
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -657,6 +753,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,
                     help="opt-in: BASELINE configs[4] paced ARKit-shape stream (e.g. 60), prints latency percentiles instead")
+    ap.add_argument("--sustained", type=int, default=0,
+                    help="opt-in: BASELINE configs[2] long stream (e.g. 1000 frames) through the host-buffer call")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"],
                     help="tile shard boundary exchange: one NCCL all-gather per epoch (default) or sender-routed stores "
                          "into the peers' inboxes over NVLink (csrc/bnv_p2p.cu)")
@@ -672,6 +770,8 @@ def main():
         run_reference(args)
     elif args.paced_fps > 0:
         run_paced(args)
+    elif args.sustained > 0:
+        run_sustained(args)
     else:
         run_b200(args)
 

@@ -65,6 +65,9 @@ SIGNATURES = {
     "bnv_map_insert": (C.c_int, [_P, _P, _P, _P, _P, _I64, _P]),
     "bnv_map_export": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "bnv_map_count_optim": (C.c_int, [_P, _P, _I64, _P, _I64, _P]),
+    "bnv_map_count_optim_queries": (C.c_int, [_P, _P, _I64, C.c_int, _P, _I64, _P]),
+    "bnv_ray_samples": (C.c_int, [_P, _P, _I64, _P, _P, _P, C.c_int, _P, C.c_int, C.c_double, _P, _P]),
+    "bnv_ray_sdf_loss": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P, C.c_double, _P, _P, _P]),
     "bnv_backproject": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, _P, _P]),
     "bnv_encode_points": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "bnv_integrate": (C.c_int, [_P, _P, _P, _P, _I64, _P]),

@@ -11,6 +11,7 @@ replaces, in sys.modules,
     third_parties.fusion                   -> TSDFVolume               (bnv_fusion_b200.tsdf)
     src.utils.voxel_utils                  -> get_world_range / flatten / unflatten (+ the reference's
                                               own remaining helpers when the reference tree is importable)
+    src.utils.render_utils.calculate_loss  -> calculate_loss           (bnv_fusion_b200.render)
 
 and registers light parent packages (src, src.models, src.models.fusion, third_parties) whose __path__
 still points into the reference tree, so everything OFF the hot path (datasets, hydra/rich helpers,
@@ -90,6 +91,22 @@ def install(reference_root: str | None = None):
     sys.modules[tf.__name__] = tf
     tp.fusion = tf
 
+    # calculate_loss: with a reference root the reference's render_utils module is loaded (its other helpers stay) and
+    # only calculate_loss is replaced; without one a bare module with the B200 function is registered
+    from .. import render
+    ru = None
+    if root and os.path.exists(os.path.join(root, "src", "utils", "render_utils.py")):
+        import importlib
+        try:
+            ru = importlib.import_module("src.utils.render_utils")
+        except ImportError:
+            ru = None
+    if ru is None:
+        ru = types.ModuleType("src.utils.render_utils")
+        sys.modules[ru.__name__] = ru
+    ru.calculate_loss = render.calculate_loss
+    utils.render_utils = ru
+
     vu = _voxel_utils_module()
     if root:
         # the reference's remaining helpers (get_frustrum_range, depth_to_tsdf, ...): executed from the reference file
@@ -111,4 +128,4 @@ def install(reference_root: str | None = None):
     if root and root not in sys.path:
         sys.path.insert(0, root)
     return {"src.models.fusion.local_point_fusion": lpf, "src.models.sparse_volume": sv, "third_parties.fusion": tf,
-            "src.utils.voxel_utils": vu}
+            "src.utils.voxel_utils": vu, "src.utils.render_utils": ru}

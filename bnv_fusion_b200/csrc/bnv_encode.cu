@@ -116,7 +116,34 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     grid_dependency_wait();                                                  // the previous frame's finalize
     const int u = u0 + lane, v = v0 + warp;
     pix = v * src.cam.W + u;
-    if (u < src.cam.W && v < src.cam.H && !(dbg & 4)) valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
+    bool foreign = false;
+    if (u < src.cam.W && v < src.cam.H && !(dbg & 4)) {
+      if (g.world > 1) {
+        // Tile shard: every rank sees every pixel, but only ~1/world of them land in its bricks.  A float32 estimate
+        // of the point (error ~1e-4 voxel) is enough to tell when the whole 2 x 2 x 2 corner block, padded by a full
+        // voxel, lies inside ONE brick of another rank: the float64 back-projection is skipped for those pixels.
+        const float zf = (float)tile.z[warp + 1][lane + 1];
+        if (zf > 0.f) {
+          const float xf = (float)tile.ax[lane + 1] * zf, yf = (float)tile.ay[warp + 1] * zf;
+          int lo[3], hi[3];
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const float w = src.cam.T[r * 4] * xf + src.cam.T[r * 4 + 1] * yf + src.cam.T[r * 4 + 2] * zf + src.cam.T[r * 4 + 3];
+            const float cv = (w - g.bmin[r]) * g.inv_vs;
+            lo[r] = (int)floorf(cv - 1.05f) >> g.brick_log2;
+            hi[r] = (int)floorf(cv + 2.05f) >> g.brick_log2;
+          }
+          foreign = lo[0] == hi[0] && lo[1] == hi[1] && lo[2] == hi[2] && (lo[0] + lo[1] + lo[2]) % g.world != g.rank &&
+                    lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0;
+        }
+      }
+      if (foreign) valid = true;                 // a valid pixel (frame statistic) that contributes no row here
+      else valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
+    }
+    if (foreign) {                               // park it outside the bounds: rule A1 drops it below
+#pragma unroll
+      for (int j = 0; j < 6; ++j) p[j] = 3.0e38f;
+    }
   } else {
     const int64_t idx = (int64_t)blockIdx.x * kPreThreads + tid;
     pix = (int32_t)idx;
@@ -380,11 +407,14 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
   if ((threadIdx.x & 31) == 0 && integrated) atomicAdd(&s_integrated, integrated);
   __syncthreads();
   if (threadIdx.x == 0 && s_integrated) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 3), (unsigned long long)s_integrated);
-  // last block publishes the frame statistics and re-arms the counters
+  // last block publishes the frame statistics and re-arms the counters.  Only thread 0 needs the fence: the one thing
+  // the last block reads from the others is the statistics atomic that thread 0 itself issued above (a fence executed
+  // by all 256 threads of every block was 30 % of this kernel's stall samples, profiles/r2b)
   __shared__ bool last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(&m.ctr[3], 1) == (int)gridDim.x - 1;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(&m.ctr[3], 1) == (int)gridDim.x - 1;
+  }
   __syncthreads();
   if (last && threadIdx.x == 0) {
     __threadfence();

@@ -151,6 +151,29 @@ __global__ void count_optim_mark_kernel(MapDev m, const float* __restrict__ nbr,
   if (slot >= 0 && slot < n_rows) flags[slot] = 1;
 }
 
+// the same for the 8 floor/ceil corners of query points (render_with_rays, src/utils/render_utils.py:494-496:
+// coords = (pts - min_coords) / voxel_size; get_neighbors; count_optim) without materialising the [8 Q, 3] corner tensor
+__global__ void count_optim_mark_queries_kernel(MapDev m, const float* __restrict__ q, int64_t n, int is_coords,
+                                                int32_t* __restrict__ flags, int64_t n_rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float v = q[i * 3 + a];
+    const float c = is_coords ? v : __fmul_rn(__fsub_rn(v, m.g.bmin[a]), m.g.inv_vs);
+    lo[a] = (long long)floorf(c);
+    hi[a] = (long long)ceilf(c);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int32_t flat;
+    if (!key_to_flat(m.g, (k & 1) ? hi[0] : lo[0], (k & 2) ? hi[1] : lo[1], (k & 4) ? hi[2] : lo[2], flat)) continue;
+    const int32_t slot = m.table[flat];
+    if (slot >= 0 && slot < n_rows) flags[slot] = 1;
+  }
+}
+
 __global__ void count_optim_apply_kernel(int32_t* __restrict__ flags, float* __restrict__ w, int64_t n_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
@@ -468,6 +491,17 @@ int bnv_map_export(bnv_map_t* m, int64_t n, int64_t* coords, float* feats, float
   if (n == 0) return BNV_OK;
   map_export_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->d, n, coords, feats, weights, hits);
   BNV_LAUNCH_CHECK("map_export_kernel");
+  return BNV_OK;
+}
+
+int bnv_map_count_optim_queries(bnv_map_t* m, const float* coords, int64_t n, int is_coords, float* weights_rows,
+                                int64_t n_rows, void* stream) {
+  if (!m || n < 0 || n_rows < 0 || n_rows > m->d.cap || (n > 0 && (!coords || !weights_rows))) { set_error("bnv_map_count_optim_queries: bad argument"); return BNV_E_ARG; }
+  if (n == 0 || n_rows == 0) return BNV_OK;
+  count_optim_mark_queries_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->d, coords, n, is_coords, m->flags, n_rows);
+  BNV_LAUNCH_CHECK("count_optim_mark_queries_kernel");
+  count_optim_apply_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(m->flags, weights_rows, n_rows);
+  BNV_LAUNCH_CHECK("count_optim_apply_kernel");
   return BNV_OK;
 }
 

@@ -141,6 +141,12 @@ int bnv_map_export(bnv_map_t* map, int64_t n, int64_t* coords_dev, float* feats_
 int bnv_map_count_optim(bnv_map_t* map, const float* nbr_coords_dev, int64_t n, float* weights_rows_dev,
                         int64_t n_rows, void* stream);
 
+/* The same for the 8 floor/ceil corners of n query points (render_with_rays, src/utils/render_utils.py:494-496:
+ * `coords = get_neighbors((pts - min_coords) / voxel_size); volume.count_optim(coords)`), without the [8 n, 3] tensor.
+ * coords_dev [n,3] fp32: voxel units if is_coords, else world. */
+int bnv_map_count_optim_queries(bnv_map_t* map, const float* coords_dev, int64_t n, int is_coords,
+                                float* weights_rows_dev, int64_t n_rows, void* stream);
+
 /* ---- per-frame local fusion -----------------------------------------------------------------
  * bnv_backproject: the dataset-side arithmetic of FusionInferenceAbstractDataset.__getitem__
  * (src/datasets/fusion_inference_dataset.py:52-74; load_depth, src/utils/common.py:86-120;
@@ -213,6 +219,25 @@ int bnv_decode_sdf_backward(bnv_map_t* map, const float* coords_dev, int64_t n_q
                             const float* feats_rows_dev, const float* weights_rows_dev, int64_t n_rows,
                             const bnv_mlp_t* dec, int min_pts, const float* grad_out_dev,
                             float* grad_feats_rows_dev, void* stream);
+
+/* ---- global optimisation step ---------------------------------------------------
+ * calculate_loss (src/utils/render_utils.py:559-594) around the decode: with bnv_map_count_optim_queries,
+ * bnv_decode_sdf and bnv_decode_sdf_backward, one inner step of NeuralMap.optimize (src/run_e2e.py:111-156) is five
+ * launches instead of ~100 small PyTorch kernels.
+ * bnv_ray_samples: get_camera_params (:426-458) + hierarchical_sampling (:190-233) -- uv_dev [n,2] pixel coordinates,
+ *   gt_pts_dev [n,3] world, K_host [9], T_wc_host [16]; t_fine_dev [n,n_fine] / t_coarse_dev [n,n_coarse] are the
+ *   uniform draws of stratified_sampling (:91); pts_dev [n, n_fine + n_coarse, 3] world points (fine samples first:
+ *   the reference sorts each ray's samples by distance, which the loss, a sum over samples, does not see).
+ * bnv_ray_sdf_loss: compute_sdf_loss (:510-557) -- pred_sdf_dev [n,S] decoded at pts_dev; nbr_pts_dev [n,n_nbr,3],
+ *   nbr_mask_dev [n,n_nbr], ray_mask_dev [n] as the dataset delivers them; n_valid_dev = sum(mask) + 1e-4 (float32
+ *   device scalar, :576); loss_dev double device scalar (overwritten); grad_pred_dev [n,S] = d loss / d pred_sdf. */
+int bnv_ray_samples(const float* uv_dev, const float* gt_pts_dev, int64_t n_rays, const float* K_host,
+                    const float* T_wc_host, const float* t_fine_dev, int n_fine, const float* t_coarse_dev, int n_coarse,
+                    double truncated_dist, float* pts_dev, void* stream);
+int bnv_ray_sdf_loss(const float* pts_dev, const float* pred_sdf_dev, int64_t n_rays, int n_samples,
+                     const float* gt_pts_dev, const float* T_wc_host, const float* nbr_pts_dev, const float* nbr_mask_dev,
+                     int n_nbr, const float* ray_mask_dev, const float* n_valid_dev, double truncated_dist, double* loss_dev,
+                     float* grad_pred_dev, void* stream);
 
 /* The sampling half of SparseVolume.meshlize (sparse_volume.py:697-738) fused with the decode:
  * for active voxels [first, first+count) evaluate the 27 samples id + {-0.5,0,0.5}^3.
