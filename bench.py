@@ -282,6 +282,9 @@ def run_b200(args):
     if args.mlp:
         config.set_mlp_mode(args.mlp)
     lib = _lib.load()
+    if args.chain is not None:                 # profiling A/B: 1 warp-specialised chain kernels (default), 0 single-role
+        lib.bnv_debug_chain.argtypes = [C.c_int]
+        lib.bnv_debug_chain(int(args.chain))
     pk = peaks()
     sampler = ClockSampler(local)
     sampler.start()
@@ -397,6 +400,33 @@ def run_b200(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1) / args.steps
     assert int(stats_host[0]) > 0
+    # ---- the same host-buffer call, results read ONE FRAME BEHIND: frame i is enqueued before the host waits for frame
+    # i - 1's statistics, so the launch latency after each host sync is hidden (extra key; `e2e` above is the strict form)
+    stats2 = [torch.zeros(4, dtype=torch.int64).pin_memory() for _ in range(2)]
+    done2 = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def run_pipelined(first, count):
+        target = shard if shard is not None else model
+        args_ = () if shard is not None else (vol,)
+        for j in range(count):
+            i = first + j
+            _, K, T = frames[i % N_FRAMES]
+            target.fuse_depth_frame_host(*args_, host[i % N_FRAMES], K, T, spec.max_depth, stats_host=stats2[j & 1],
+                                         next_depth_mm_host=host[(i + 1) % N_FRAMES])
+            done2[j & 1].record()
+            if j > 0:
+                done2[(j - 1) & 1].synchronize()           # the user reads frame i - 1's result while frame i runs
+                assert int(stats2[(j - 1) & 1][0]) > 0
+        done2[(count - 1) & 1].synchronize()
+        assert int(stats2[(count - 1) & 1][0]) > 0
+
+    run_pipelined(0, 4)
+    barrier()
+    e0.record()
+    run_pipelined(3 * args.steps, args.steps)
+    e1.record()
+    barrier()
+    e2e_pipe_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop()
     vol.check_status()
     # ---- reference "local" timer scope: neural fusion + coarse TSDF prior (run_e2e.py:78-109) -----------
@@ -481,6 +511,7 @@ def run_b200(args):
         n_q_job, dec_ms_job = float(t[0]), maxr(dec_ms)
     ms = maxr(float(np.sum(step_ms))) / args.steps
     warm_ms, e2e_ms, local_ms, staged_ms = maxr(warm_ms), maxr(e2e_ms), maxr(local_ms), maxr(staged_ms)
+    e2e_pipe_ms = maxr(e2e_pipe_ms)
     enc_avg = float(np.mean(enc_ms))
     rows_per_launch = rows_total / args.steps
     enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
@@ -510,12 +541,15 @@ def run_b200(args):
                     "what": "bnv_fuse_frame_host per frame: pinned uint16 depth -> H2D (the next frame's copy is hinted and "
                             "overlaps this frame's kernels) -> fuse -> D2H frame statistics, then a host sync (the user reads "
                             "the result of every frame)"},
+            "e2e_results_one_frame_behind": {"value": 1e3 / e2e_pipe_ms, "unit": "frames/s",
+                                             "what": "same call and copies per frame as e2e, but frame i is enqueued before the host "
+                                                     "waits for frame i - 1's statistics (every frame's statistics are still read)"},
             "local_scope": {"value": 1e3 / local_ms, "unit": "frames/s", "tsdf_dims": tsdf_dims,
                             "what": "reference 'local' timer scope (run_e2e.py:250-252): neural fusion + coarse TSDF "
                                     "integration at 2.5 cm, host depth in, frame stats out"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "encode_chain_kernel (8 corner rows per point record -> encoder MLP on tcgen05 -> scatter-add)"
+            "roofline": {"kernel": "encode_ws_kernel (8 corner rows per point record -> encoder MLP on tcgen05 -> scatter-add)"
                                    if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel (fp32 CUDA cores)",
                          "bound": "tensor",
                          "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
@@ -749,6 +783,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chain", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--ref-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,

@@ -219,11 +219,8 @@ static int decode_common(bnv_map_t* map, DecArgs& a, const bnv_mlp_t* dec, int m
   if (a.n_queries == 0) return BNV_OK;
   if (mode == BNV_MLP_TC16) return bnv_internal_decode_tc(map, a, dec, s);
   if (mode != BNV_MLP_FP32) { set_error("decode: unknown MLP mode %d", mode); return BNV_E_ARG; }
-  static bool attr = false;
-  if (!attr) {
-    BNV_CUDA(cudaFuncSetAttribute(decode_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
-    attr = true;
-  }
+  // per device and cheap: set on every call rather than cached per process
+  BNV_CUDA(cudaFuncSetAttribute(decode_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDecSmem));
   decode_simt_kernel<<<(unsigned)((a.n_queries + kDecThreads - 1) / kDecThreads), kDecThreads, kDecSmem, s>>>(
       map->d, a, bnv_internal_simt_weights(dec));
   BNV_LAUNCH_CHECK("decode_simt_kernel");
@@ -250,11 +247,8 @@ int bnv_decode_sdf_backward(bnv_map_t* map, const float* coords, int64_t n_queri
   if (!dec || dec->n_in != 17 || dec->n_out != 1) { set_error("decode backward: decoder MLP must be 17 -> 1"); return BNV_E_ARG; }
   if (n_rows <= 0 || n_rows > map->d.cap || !feats_rows || !weights_rows) { set_error("decode backward: bad exported rows"); return BNV_E_ARG; }
   if (n_queries == 0) return BNV_OK;
-  static bool attr = false;
-  if (!attr) {
-    BNV_CUDA(cudaFuncSetAttribute(decode_backward_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-    attr = true;
-  }
+  // per device and cheap: set on every call rather than cached per process
+  BNV_CUDA(cudaFuncSetAttribute(decode_backward_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
   decode_backward_simt_kernel<<<(unsigned)((n_queries + kDecThreads - 1) / kDecThreads), kDecThreads, kBwdSmem,
                                 (cudaStream_t)stream>>>(map->d, a, dec->w32, dec->wraw, grad_out, grad_feats_rows);
   BNV_LAUNCH_CHECK("decode_backward_simt_kernel");

@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
       // publish the dense row in the entry's high word (visible to the kernels that follow) and its key
       reinterpret_cast<int32_t*>(m.ftable + pr[j].x)[1] = row;
       m.fkeys[row] = pr[j].x;
+      // finalize will look this voxel up in the persistent table two kernels from now: pull the line into L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + pr[j].x));
       ++row;
     }
   if (keep && !(dbg & 8)) {

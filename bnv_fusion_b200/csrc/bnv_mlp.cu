@@ -40,11 +40,8 @@ template <int NIN, int NOUT>
 static int launch_forward(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s) {
   using M = SimtMlp<NIN, NOUT>;
   const size_t smem = (size_t)(M::kFloats + 64 * 256) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    BNV_CUDA(cudaFuncSetAttribute(mlp_forward_simt_kernel<NIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  // per device and cheap: set on every call rather than cached per process
+  BNV_CUDA(cudaFuncSetAttribute(mlp_forward_simt_kernel<NIN, NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mlp_forward_simt_kernel<NIN, NOUT><<<(unsigned)((n + 255) / 256), 256, smem, s>>>(mlp->w32, x, n, y);
   BNV_LAUNCH_CHECK("mlp_forward_simt_kernel");
   return BNV_OK;

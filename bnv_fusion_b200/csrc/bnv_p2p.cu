@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(MapDev m, const int32_t*
 __global__ void __launch_bounds__(256) insert_inbox_kernel(MapDev m, PeerPtrs peers, int buf, uint32_t seq, int64_t cap,
                                                            int32_t* __restrict__ done) {
   const GeomDev& g = m.g;
+  if (m.ctr[2] & kErrExchange) return;     // a peer's records never arrived (latched by wait_flags_kernel): no upsert, no ack
   int32_t* base = peers.base[g.rank];
   const unsigned gmask = 0xFFu << ((threadIdx.x & 31) & ~7);
   const int lane8 = threadIdx.x & 7;
@@ -211,7 +212,12 @@ int bnv_exchange_create(bnv_exchange_t** out, bnv_map_t* map, int64_t capacity_r
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ex->side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->fused, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ex->upserted, cudaEventDisableTiming);
-  if (e != cudaSuccess) { set_error("bnv_exchange_create: %s", cudaGetErrorString(e)); return BNV_E_ALLOC; }
+  if (e != cudaSuccess) {
+    set_error("bnv_exchange_create: %s", cudaGetErrorString(e));
+    ex->world = 0;                          // nothing was opened on peers
+    bnv_exchange_destroy(ex);
+    return BNV_E_ALLOC;
+  }
   BNV_CUDA(cudaDeviceSynchronize());
   ex->peers.base[rank] = ex->block;
   *out = ex;

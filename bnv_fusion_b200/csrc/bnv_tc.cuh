@@ -166,6 +166,15 @@ __device__ __forceinline__ void tmem_ld32_pack16(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -390,17 +399,19 @@ __device__ __forceinline__ void chain_wait_d(RowChain& c) {
 }
 
 __device__ __forceinline__ void chain_epilogue(RowChain& c) {
+  // two half-tiles: the second 32-column load is in flight while the first half is converted and stored
   uint32_t v[32], w[32];
   tmem_ld32(c.t_d, v);
-  tmem_ld32(c.t_d + 32, w);
   tmem_wait_ld();
-  uint32_t a[32];
+  tmem_ld32(c.t_d + 32, w);
+  uint32_t a[16], b[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    a[i] = pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
-    a[16 + i] = pack_relu_f16x2(w[2 * i], w[2 * i + 1]);
-  }
-  tmem_st32(c.t_a, a);
+  for (int i = 0; i < 16; ++i) a[i] = pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
+  tmem_st16(c.t_a, a);
+  tmem_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) b[i] = pack_relu_f16x2(w[2 * i], w[2 * i + 1]);
+  tmem_st16(c.t_a + 16, b);
 }
 
 // hidden part of the current item (its L0 is in flight): L0 -> L1 -> L2 -> h3 stored.  `shadow1()` runs

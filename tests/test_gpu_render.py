@@ -66,10 +66,12 @@ def test_calculate_loss_matches_reference_autograd(golden_dir, model, dev, mode)
     bad = np.abs(grad - ref_grad).max(1) > (1e-4 if mode == "fp32" else 2e-2) * scale
     assert bad.mean() <= 0.002, (bad.sum(), np.abs(grad - ref_grad).max(), scale)
     assert (np.abs(grad).sum(1) > 0).sum() > 1000
-    # Adam step like NeuralMap.optimize: the features move and the loss of the same draws goes down
-    opt = torch.optim.Adam([vol.features], lr=0.001)
-    opt.step()
-    opt.zero_grad()
+    # a small step against the gradient lowers the loss of the same draws (weights reset first: count_optim is a side
+    # effect of every call and would change the validity masks)
+    with torch.no_grad():
+        vol.features -= 2e-3 * vol.features.grad / vol.features.grad.abs().max()
+        vol.weights.copy_(torch.from_numpy(g["weights_before"][perm]).to(dev))
+    vol.features.grad = None
     again = calculate_loss(vol, rays, model.nerf, 10, 0.05, 3, sdf_delta=delta, t_rand=t_rand)["depth_bce_loss"]
-    assert float(again) < float(loss)
+    assert float(again) < float(loss), (float(again), float(loss))
     config.set_mlp_mode("tc16")
