@@ -282,9 +282,6 @@ def run_b200(args):
     if args.mlp:
         config.set_mlp_mode(args.mlp)
     lib = _lib.load()
-    if args.chain is not None:                 # profiling A/B: 1 warp-specialised chain kernels (default), 0 single-role
-        lib.bnv_debug_chain.argtypes = [C.c_int]
-        lib.bnv_debug_chain(int(args.chain))
     pk = peaks()
     sampler = ClockSampler(local)
     sampler.start()
@@ -554,7 +551,7 @@ def run_b200(args):
                          "bound": "tensor",
                          "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                          "frac": enc_tflops / pk["tf_burst"],
-                         "traffic": traffic("encode_chain_kernel" if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
+                         "traffic": traffic("encode_ws_kernel" if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
                          "peak_source": pk["src"],
                          "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "prepass_ms": pre_avg, "finalize_ms": fin_avg,
                          "timing": "CUDA events around every kernel over a second pass of the same K cold steps "
@@ -575,7 +572,7 @@ def run_b200(args):
                        "roofline": {"bound": "tensor", "achieved": exe_tflops, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                                     "frac": exe_tflops / pk["tf_sustained"], "frac_of_burst_peak": exe_tflops / pk["tf_burst"],
                                     "algorithmic_tflops": dec_tflops,
-                                    "traffic": ((traffic("gtable_tc_kernel") or 0) + (traffic("blend_blocks_kernel") or 0)) or None
+                                    "traffic": ((traffic("gtable_ws_kernel") or 0) + (traffic("blend_blocks_kernel") or 0)) or None
                                                if config.mlp_mode_name() == "tc16" else traffic("decode_simt_kernel"),
                                     "peak_source": pk["src"],
                                     "note": "achieved = FLOPs executed on the tensor pipe over the time of BOTH kernels (G table + "
@@ -588,7 +585,7 @@ def run_b200(args):
                                    "roofline": {"bound": "tensor", "achieved": gen_tflops, "peak": pk["tf_sustained"],
                                                 "unit": "TFLOP/s", "frac": gen_tflops / pk["tf_sustained"],
                                                 "frac_of_burst_peak": gen_tflops / pk["tf_burst"],
-                                                "traffic": traffic("decode_tc_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel")}}},
+                                                "traffic": traffic("decode_ws_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel")}}},
             "cpu_baseline": cpu,
         }
         if parity is not None:
@@ -783,7 +780,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--chain", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--ref-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,

@@ -11,8 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# BNV_LIB: profiling builds only (tools/chain_phase_profile.py loads the -DBNV_CHAIN_PROFILE=1 variant)
-LIB_PATH = os.environ.get("BNV_LIB") or os.path.join(_HERE, "libbnv_b200.so")
+LIB_PATH = os.path.join(_HERE, "libbnv_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MLP_FP32 = 0

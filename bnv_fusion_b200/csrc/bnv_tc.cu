@@ -125,28 +125,18 @@ int bnv_internal_pack_tc_weights(bnv_mlp_t* mlp, const float* params) {
   return BNV_OK;
 }
 
-// chain kernels (bnv_tc_chain.cu)
-int bnv_internal_mlp_forward_chain(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s);
-int bnv_internal_encode_chain(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
-int bnv_internal_decode_chain(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s);
-int bnv_internal_gtable_chain(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s);
-
-// warp-specialised kernels (bnv_tc_ws.cu)
+// warp-specialised chain kernels (bnv_tc_ws.cu)
+int bnv_internal_mlp_forward_ws(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s);
 int bnv_internal_encode_ws(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s);
 int bnv_internal_decode_ws(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s);
-
-// 1 (default): warp-specialised chain kernels; 0: the single-role kernels of bnv_tc_chain.cu.  Profiling A/B only
-// (tools/, bench.py --chain): not part of the ABI header.
-static int g_chain_variant = 1;
-extern "C" int bnv_debug_chain(int variant) { g_chain_variant = variant; return BNV_OK; }
+int bnv_internal_gtable_ws(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s);
 
 int bnv_internal_mlp_forward_tc(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s) {
-  return bnv_internal_mlp_forward_chain(mlp, x, n, y, s);
+  return bnv_internal_mlp_forward_ws(mlp, x, n, y, s);
 }
 
 int bnv_internal_encode_tc(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, cudaStream_t s) {
-  if (g_chain_variant == 1) return bnv_internal_encode_ws(map, max_records, enc, s);
-  return bnv_internal_encode_chain(map, max_records, enc, s);
+  return bnv_internal_encode_ws(map, max_records, enc, s);
 }
 
 int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_t* dec, cudaStream_t s) {
@@ -161,12 +151,11 @@ int bnv_internal_decode_tc(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_
       set_error("decode: G table of %lld rows exceeds the map's capacity", (long long)a.n_rows);
       return BNV_E_CAPACITY;
     }
-    int rc = bnv_internal_gtable_chain(map, a.n_rows, dec, s);
+    int rc = bnv_internal_gtable_ws(map, a.n_rows, dec, s);
     if (rc) return rc;
     blend_blocks_kernel<<<(unsigned)((a.n_queries / 27 + 7) / 8), 256, 0, s>>>(map->d, a, (const float*)map->gtable);   // one warp per voxel
     BNV_LAUNCH_CHECK("blend_blocks_kernel");
     return BNV_OK;
   }
-  if (g_chain_variant == 1) return bnv_internal_decode_ws(map, a, dec, s);
-  return bnv_internal_decode_chain(map, a, dec, s);
+  return bnv_internal_decode_ws(map, a, dec, s);
 }

@@ -96,6 +96,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// wait of a latency-tolerant warp: the hardware may keep the thread suspended for up to `hint_ns` per attempt, so a
+// waiting warp does not compete for issue slots with the warps on the critical path
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  }
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -223,51 +237,10 @@ __device__ __forceinline__ uint32_t pack_relu_f16x2(uint32_t lo_bits, uint32_t h
 
 __device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); }
 
-// =================================================================================================
-// The software-pipelined chain.  Per item (one 128-row tile through the 4-layer MLP):
-//
-//   L0 -> epi -> L1 -> [shadow] -> epi -> L2 -> epi -> { L3 (N = 16) + L0 of the NEXT item, one issue burst }
-//
-// The output layer also runs on the tensor core (h3 rounded to fp16 like every other activation) and
-// is never waited for on the critical path: its 16 result columns are read in the shadow of the next
-// item (or after the loop), so an item costs three exposed MMA round trips instead of four (encoder)
-// or three plus a 144-instruction CUDA-core output layer (decoder).
-//
 // TMEM slot of a chain (128 columns): D [0,64) fp32 | A_h [64,96) packed fp16 hidden activations |
 // A_in [96,112) packed fp16 input row of the next item | D_out [112,128) fp32 output layer.
-// =================================================================================================
 constexpr int kInCol = 96;
 constexpr int kOutCol = 112;
-
-// Optional phase timers of the chain (make EXTRA=-DBNV_CHAIN_PROFILE=1, tools/chain_phase_profile.py): thread 0 of
-// every warpgroup accumulates clock64 deltas per phase into a per-translation-unit device array.  With the macro
-// off (default) the hooks expand to nothing.
-#ifndef BNV_CHAIN_PROFILE
-#define BNV_CHAIN_PROFILE 0
-#endif
-#if BNV_CHAIN_PROFILE
-static __device__ unsigned long long g_chain_prof[16];
-__device__ __forceinline__ long long prof_clk() {
-  long long t;
-  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
-  return t;
-}
-#define BNV_PROF_MARK(t) const long long t = ::bnv::tc::prof_clk()
-#define BNV_PROF_ADD(i, t0)                                                                                     \
-  do {                                                                                                          \
-    if ((threadIdx.x & 127) == 0) atomicAdd(&::bnv::tc::g_chain_prof[i], (unsigned long long)(::bnv::tc::prof_clk() - (t0))); \
-  } while (0)
-#define BNV_PROF_COUNT(i)                                                           \
-  do {                                                                              \
-    if ((threadIdx.x & 127) == 0) atomicAdd(&::bnv::tc::g_chain_prof[i], 1ull);     \
-  } while (0)
-#else
-#define BNV_PROF_MARK(t)
-#define BNV_PROF_ADD(i, t0)
-#define BNV_PROF_COUNT(i)
-#endif
-// phase indices: 0 wait L0 | 1 epilogue+issue L1 | 2 shadow1 | 3 wait L1 | 4 epilogue+issue L2 | 5 shadow2 |
-// 6 wait L2 | 7 epilogue 3 | 8 finish (issue L3 + next L0) | 9 per-tile precompute | 10 lifetime | 11 items
 
 // floor (0) / ceil (1) flavour of corner k per axis, get_neighbors' order (src/models/fusion/utils.py:98-167):
 // k: (f,f,f) (c,f,f) (f,c,f) (f,f,c) (c,c,f) (c,f,c) (f,c,c) (c,c,c)
@@ -283,224 +256,6 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
-}
-
-struct RowChain {
-  uint32_t t_d, t_a, t_in, t_o;  // this warp's lane base at the slot's D / A_h / A_in / D_out columns
-  uint32_t d_slot;               // slot base (lane 0), for the issuing thread
-  uint64_t* bar_d;               // hidden-layer D complete
-  uint64_t* bar_o;               // output-layer D complete
-  uint32_t par_d, par_o;
-  uint32_t w_saddr;
-  int bar_id;
-  bool issuer_warp;              // warp-uniform: this warp issues the warpgroup's UMMAs (one elected lane)
-};
-
-template <int NWG>
-struct TcShared {
-  uint64_t bar_d[NWG];
-  uint64_t bar_o[NWG];
-  uint64_t bar_w;                // weight image arrived (cp.async.bulk complete_tx)
-  uint32_t tmem_base;
-  uint32_t live[NWG][2][4];      // per-warp corner masks of the tile shard (double-buffered)
-};
-
-template <int NWG>
-__device__ __forceinline__ RowChain tc_setup(TcShared<NWG>& sh, uint8_t* s_weights, const uint8_t* __restrict__ g_weights,
-                                               int w_bytes) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-  // weight image -> shared memory with ONE bulk async copy (TMA engine, cp.async.bulk: no registers, no per-thread
-  // loads) that signals an mbarrier with its byte count; barrier init and TMEM allocation overlap the transfer
-  if (tid == 0) {
-#pragma unroll
-    for (int g = 0; g < NWG; ++g) {
-      mbar_init(&sh.bar_d[g], 1);
-      mbar_init(&sh.bar_o[g], 1);
-    }
-    mbar_init(&sh.bar_w, 1);
-    mbar_fence_init();
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&sh.bar_w)), "r"((uint32_t)w_bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(s_weights)), "l"(g_weights), "r"((uint32_t)w_bytes), "r"(smem_u32(&sh.bar_w))
-                 : "memory");
-  }
-  if (warp == 0) tmem_alloc(&sh.tmem_base, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  mbar_wait(&sh.bar_w, 0);                 // the weights have landed (async proxy writes, made visible by the mbarrier)
-  RowChain c;
-  // warp-uniform values are broadcast with shfl so that the compiler can keep them in uniform registers
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0), wg_u = warp_u >> 2;
-  c.d_slot = __shfl_sync(0xffffffffu, sh.tmem_base, 0) + wg_u * kSlotCols;
-  c.t_d = c.d_slot + ((uint32_t)((warp_u & 3) * 32) << 16);
-  c.t_a = c.t_d + kACol;
-  c.t_in = c.t_d + kInCol;
-  c.t_o = c.t_d + kOutCol;
-  c.bar_d = &sh.bar_d[wg_u];
-  c.bar_o = &sh.bar_o[wg_u];
-  c.par_d = c.par_o = 0;
-  c.w_saddr = smem_u32(s_weights);
-  c.bar_id = 1 + wg_u;
-  // issuing warps of the four chains sit in different SM sub-partitions (warp % 4)
-  c.issuer_warp = (warp_u & 3) == (wg_u & 3);
-  return c;
-}
-
-template <int NWG>
-__device__ __forceinline__ void tc_teardown(TcShared<NWG>& sh) {
-  tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh.tmem_base, 512);
-}
-
-// one K-step of layer (K-major B block at b0, N columns): D[d_col] (+)= A[a_col + 8 kk] * B
-template <int N>
-__device__ __forceinline__ void umma_step(const RowChain& c, uint32_t b0, int d_col, int a_col, int kk) {
-  constexpr uint32_t lbo = (uint32_t)(N / 8) * 128u;
-  umma_ts_f16(c.d_slot + d_col, c.d_slot + a_col + kk * 8, smem_desc_kmajor(b0 + kk * 2 * lbo, lbo, 128),
-              idesc_f16_m128(N), kk > 0 ? 1u : 0u);
-}
-
-// every thread's TMEM stores / loads of this step are done -> the warpgroup's issuer runs `f`
-template <class F>
-__device__ __forceinline__ void chain_sync_issue(RowChain& c, F&& f) {
-  tmem_wait_st();
-  tc_fence_before();
-  wg_sync(c.bar_id);
-  if (c.issuer_warp) {
-    tc_fence_after();
-    if (elect_one()) f();
-  }
-}
-
-// stage the input row of the next item (INW packed fp16x2 words, ones-padded); A_in is free as soon as
-// the L0 of the current item has completed, i.e. any time after the item's first epilogue
-template <int INW>
-__device__ __forceinline__ void chain_stage(RowChain& c, const uint32_t (&in)[INW]) {
-  static_assert(INW == 8 || INW == 16, "in_pad must be 16 or 32");
-  if constexpr (INW == 8) tmem_st8(c.t_in, in); else tmem_st16(c.t_in, in);
-}
-
-// first item of a sequence: L0 alone
-template <int INW>
-__device__ __forceinline__ void chain_begin(RowChain& c) {
-  chain_sync_issue(c, [&]() {
-#pragma unroll
-    for (int kk = 0; kk < INW / 8; ++kk) umma_step<64>(c, c.w_saddr, 0, kInCol, kk);
-    umma_commit(c.bar_d);
-  });
-}
-
-__device__ __forceinline__ void chain_wait_d(RowChain& c) {
-  mbar_wait(c.bar_d, c.par_d);
-  c.par_d ^= 1;
-  tc_fence_after();
-}
-
-__device__ __forceinline__ void chain_epilogue(RowChain& c) {
-  // two half-tiles: the second 32-column load is in flight while the first half is converted and stored
-  uint32_t v[32], w[32];
-  tmem_ld32(c.t_d, v);
-  tmem_wait_ld();
-  tmem_ld32(c.t_d + 32, w);
-  uint32_t a[16], b[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = pack_relu_f16x2(v[2 * i], v[2 * i + 1]);
-  tmem_st16(c.t_a, a);
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) b[i] = pack_relu_f16x2(w[2 * i], w[2 * i + 1]);
-  tmem_st16(c.t_a + 16, b);
-}
-
-// hidden part of the current item (its L0 is in flight): L0 -> L1 -> L2 -> h3 stored.  `shadow1()` runs
-// right after L1 has been issued, `shadow2()` right after L2: consume the previous item's output
-// (chain_output) and issue the next item's loads in the first, stage the next item's input
-// (chain_stage) in the second -- the loads then have a whole round trip to land.
-template <int INW, class Shadow1, class Shadow2>
-__device__ __forceinline__ void chain_hidden(RowChain& c, Shadow1&& shadow1, Shadow2&& shadow2) {
-  constexpr int off1 = 2 * INW * 64 * 2, off2 = off1 + 64 * 64 * 2;
-  BNV_PROF_MARK(p0);
-  chain_wait_d(c);
-  BNV_PROF_ADD(0, p0);
-  BNV_PROF_MARK(p1);
-  chain_epilogue(c);
-  chain_sync_issue(c, [&]() {
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off1, 0, kACol, kk);
-    umma_commit(c.bar_d);
-  });
-  BNV_PROF_ADD(1, p1);
-  BNV_PROF_MARK(p2);
-  shadow1();
-  BNV_PROF_ADD(2, p2);
-  BNV_PROF_MARK(p3);
-  chain_wait_d(c);
-  BNV_PROF_ADD(3, p3);
-  BNV_PROF_MARK(p4);
-  chain_epilogue(c);
-  chain_sync_issue(c, [&]() {
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) umma_step<64>(c, c.w_saddr + off2, 0, kACol, kk);
-    umma_commit(c.bar_d);
-  });
-  BNV_PROF_ADD(4, p4);
-  BNV_PROF_MARK(p5);
-  shadow2();
-  BNV_PROF_ADD(5, p5);
-  BNV_PROF_MARK(p6);
-  chain_wait_d(c);
-  BNV_PROF_ADD(6, p6);
-  BNV_PROF_MARK(p7);
-  chain_epilogue(c);
-  BNV_PROF_ADD(7, p7);
-}
-
-// output layer of the current item + (has_next) L0 of the staged next item, interleaved in one burst:
-// the two accumulate into different TMEM columns, so their K-steps do not serialise on each other
-template <int INW>
-__device__ __forceinline__ void chain_finish(RowChain& c, bool has_next) {
-  constexpr int off3 = 2 * INW * 64 * 2 + 2 * 64 * 64 * 2;
-  BNV_PROF_MARK(p8);
-  chain_sync_issue(c, [&]() {
-    if (has_next) {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        umma_step<16>(c, c.w_saddr + off3, kOutCol, kACol, kk);
-        if (kk < INW / 8) umma_step<64>(c, c.w_saddr, 0, kInCol, kk);
-      }
-      umma_commit(c.bar_o);
-      umma_commit(c.bar_d);
-    } else {
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) umma_step<16>(c, c.w_saddr + off3, kOutCol, kACol, kk);
-      umma_commit(c.bar_o);
-    }
-  });
-  BNV_PROF_ADD(8, p8);
-  BNV_PROF_COUNT(11);
-}
-
-// read the NOUT outputs of the item whose chain_finish was issued last (waits for its output layer)
-template <int NOUT>
-__device__ __forceinline__ void chain_output(RowChain& c, float (&out)[NOUT]) {
-  static_assert(NOUT == 8 || NOUT == 1, "n_out must be 8 or 1");
-  mbar_wait(c.bar_o, c.par_o);
-  c.par_o ^= 1;
-  tc_fence_after();
-  if constexpr (NOUT == 8) {
-    uint32_t r[8];
-    tmem_ld8(c.t_o, r);
-    tmem_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = __uint_as_float(r[j]);
-  } else {
-    uint32_t r;
-    tmem_ld1(c.t_o, r);
-    tmem_wait_ld();
-    out[0] = __uint_as_float(r);
-  }
 }
 
 }  // namespace tc

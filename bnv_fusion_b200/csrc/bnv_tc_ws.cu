@@ -297,6 +297,104 @@ __global__ void __launch_bounds__(kThreads, 1) decode_ws_kernel(MapDev m, DecArg
   ws_teardown(S.sh);
 }
 
+// ---- factored decode of the meshlize sample blocks: G[V][l] table (see bnv_tc.cu) ----------------------
+// rows = (exported voxel V, offset l of the 27): items = 128-row tiles; the helper builds each row from the voxel's
+// packed features and the three per-axis word pairs of l = -0.5, 0, +0.5, and stores the MLP outputs into G
+__global__ void __launch_bounds__(kThreads, 1) gtable_ws_kernel(const uint4* __restrict__ packed, int64_t n_rows,
+                                                                 const uint8_t* __restrict__ gW, int w_bytes,
+                                                                 float* __restrict__ G) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  SmemBase& S = *reinterpret_cast<SmemBase*>(smem);
+  Role c = ws_setup(S.sh, weights_smem(smem), gW, w_bytes);
+  if (!c.helper) {
+    e_run<16>(c);
+  } else {
+    const int64_t total = (n_rows + 1) * 27;                       // voxel n_rows = the miss voxel
+    const int64_t n_tiles = (total + 127) / 128;
+    uint32_t w_ls[3], w_c1[3];                                     // l = -0.5, 0, +0.5
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float l = 0.5f * (float)(d - 1);
+      float sn, cs;
+      __sincosf(l, &sn, &cs);
+      w_ls[d] = pack_f16x2(l, sn);
+      w_c1[d] = pack_f16x2(cs, 1.0f);
+    }
+    auto consume = [&](int tile) {
+      float y[1];
+      h_read_out<1>(c, y);
+      const int64_t row = (int64_t)tile * 128 + c.row;
+      if (row < total) G[row] = y[0];
+    };
+    HelperSeq seq;
+    for (int64_t tile = (int64_t)blockIdx.x * kNC + c.chain; tile < n_tiles; tile += (int64_t)gridDim.x * kNC) {
+      const int64_t row = tile * 128 + c.row;
+      const int64_t v = row / 27;
+      const int li = (int)(row - v * 27);
+      uint4 f = make_uint4(0, 0, 0, 0);
+      if (row < total && v < n_rows) f = __ldg(packed + v);
+      const int dx = li / 9, dy = (li / 3) % 3, dz = li % 3;
+      seq.emit(
+          c, (int)tile,
+          [&]() {
+            // dynamic index into 3-element register arrays -> selects
+            const uint32_t lx = dx == 0 ? w_ls[0] : dx == 1 ? w_ls[1] : w_ls[2], cx = dx == 0 ? w_c1[0] : dx == 1 ? w_c1[1] : w_c1[2];
+            const uint32_t ly = dy == 0 ? w_ls[0] : dy == 1 ? w_ls[1] : w_ls[2], cy = dy == 0 ? w_c1[0] : dy == 1 ? w_c1[1] : w_c1[2];
+            const uint32_t lz = dz == 0 ? w_ls[0] : dz == 1 ? w_ls[1] : w_ls[2], cz = dz == 0 ? w_c1[0] : dz == 1 ? w_c1[1] : w_c1[2];
+            const uint32_t in[16] = {f.x, f.y, f.z, f.w, lx, cx, ly, cy, lz, cz, kOnes, kOnes, kOnes, kOnes, kOnes, kOnes};
+            h_stage<16>(c, in);
+          },
+          consume);
+    }
+    seq.finish(c, consume);
+  }
+  ws_teardown(S.sh);
+}
+
+// ---- plain forward (tcnnPointNetEncoder.forward / tcnnNeRFModel.geo_forward): items = 128-row tiles --------------
+template <int NIN, int INW>
+__device__ __forceinline__ void load_row(const float* __restrict__ x, int64_t i, int64_t n, uint32_t (&in)[INW]) {
+  float xi[2 * INW];
+#pragma unroll
+  for (int k = 0; k < 2 * INW; ++k) {
+    const int src = NIN == 17 ? dec_perm(k) : enc_perm(k);       // column order of the packed W0
+    xi[k] = (src < NIN && i < n) ? __ldg(x + i * NIN + src) : 1.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < INW; ++k) in[k] = pack_f16x2(xi[2 * k], xi[2 * k + 1]);
+}
+
+template <int NIN, int INW, int NOUT>
+__global__ void __launch_bounds__(kThreads, 1) mlp_forward_ws_kernel(const uint8_t* __restrict__ gW, int w_bytes,
+                                                                      const float* __restrict__ x, int64_t n,
+                                                                      float* __restrict__ y) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  SmemBase& S = *reinterpret_cast<SmemBase*>(smem);
+  Role c = ws_setup(S.sh, weights_smem(smem), gW, w_bytes);
+  if (!c.helper) {
+    e_run<INW>(c);
+  } else {
+    const int64_t n_tiles = (n + 127) / 128;
+    auto consume = [&](int tile) {
+      float out[NOUT];
+      h_read_out<NOUT>(c, out);
+      const int64_t row = (int64_t)tile * 128 + c.row;
+      if (row < n) {
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) y[row * NOUT + o] = out[o];
+      }
+    };
+    HelperSeq seq;
+    for (int64_t tile = (int64_t)blockIdx.x * kNC + c.chain; tile < n_tiles; tile += (int64_t)gridDim.x * kNC) {
+      uint32_t in[INW];
+      load_row<NIN, INW>(x, tile * 128 + c.row, n, in);
+      seq.emit(c, (int)tile, [&]() { h_stage<INW>(c, in); }, consume);
+    }
+    seq.finish(c, consume);
+  }
+  ws_teardown(S.sh);
+}
+
 }  // namespace wsk
 }  // namespace bnv
 
@@ -328,5 +426,30 @@ int bnv_internal_decode_ws(bnv_map_t* map, const bnv::DecArgs& a, const bnv_mlp_
   decode_ws_kernel<<<grid_for((a.n_queries + 127) / 128), kThreads, smem, s>>>(map->d, a, (const uint4*)map->dec_pack,
                                                                               (const uint8_t*)dec->w16, (int)dec->w16_bytes);
   BNV_LAUNCH_CHECK("decode_ws_kernel");
+  return BNV_OK;
+}
+
+int bnv_internal_gtable_ws(bnv_map_t* map, int64_t n_rows, const bnv_mlp_t* dec, cudaStream_t s) {
+  const size_t smem = weights_off() + weight_image(dec->in_pad).bytes;
+  BNV_CUDA(cudaFuncSetAttribute(gtable_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t tiles = ((n_rows + 1) * 27 + 127) / 128;
+  gtable_ws_kernel<<<grid_for(tiles), kThreads, smem, s>>>((const uint4*)map->dec_pack, n_rows, (const uint8_t*)dec->w16,
+                                                          (int)dec->w16_bytes, (float*)map->gtable);
+  BNV_LAUNCH_CHECK("gtable_ws_kernel");
+  return BNV_OK;
+}
+
+
+int bnv_internal_mlp_forward_ws(const bnv_mlp_t* mlp, const float* x, int64_t n, float* y, cudaStream_t s) {
+  const size_t smem = weights_off() + weight_image(mlp->in_pad).bytes;
+  const int grid = grid_for((n + 127) / 128);
+  if (mlp->n_in == 6) {
+    BNV_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<6, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_forward_ws_kernel<6, 8, 8><<<grid, kThreads, smem, s>>>((const uint8_t*)mlp->w16, (int)mlp->w16_bytes, x, n, y);
+  } else {
+    BNV_CUDA(cudaFuncSetAttribute(mlp_forward_ws_kernel<17, 16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_forward_ws_kernel<17, 16, 1><<<grid, kThreads, smem, s>>>((const uint8_t*)mlp->w16, (int)mlp->w16_bytes, x, n, y);
+  }
+  BNV_LAUNCH_CHECK("mlp_forward_ws_kernel");
   return BNV_OK;
 }

@@ -3,7 +3,7 @@
 #   usage: tools/gpu_profile.sh <tag> [kernel-regex]
 mkdir -p gpurun_out
 TAG=${1:-r2a}
-KERN=${2:-'frame_prepass|encode_chain|finalize_fused|decode_tc|gtable_tc|blend_blocks|tsdf_integrate'}
+KERN=${2:-'frame_prepass|encode_ws|finalize_fused|decode_ws|gtable_ws|blend_blocks|tsdf_integrate|mesh_'}
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
 timeout 400 ncu --set full --clock-control none --import-source on \
