@@ -41,8 +41,11 @@ __device__ __forceinline__ int finalize_rows(const MapDev& m, int min_pts, bool 
       const float4 a = s4[0], b = s4[1];
       s4[0] = s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float s[kFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      // float32 sums / exact integer count: one correctly rounded float32 division (the float64 form of the exact-
+      // parity mode costs ~45 instructions per feature and was 90 % of this kernel's instruction count)
+      const float fc = (float)cnt;
 #pragma unroll
-      for (int j = 0; j < kFeat; ++j) mean[j] = (float)((double)s[j] / (double)cnt);
+      for (int j = 0; j < kFeat; ++j) mean[j] = __fdiv_rn(s[j], fc);
     } else {
       longlong2* s2 = reinterpret_cast<longlong2*>(m.fsum + (size_t)t * kFeat);
 #pragma unroll
@@ -114,13 +117,12 @@ __device__ __forceinline__ void finalize_publish(const MapDev& m, int integrated
   // last block publishes the frame statistics and re-arms the counters.  Only thread 0 needs the fence: the one thing
   // the last block reads from the others is the statistics atomic that thread 0 itself issued above (a fence executed
   // by all 256 threads of every block was 30 % of this kernel's stall samples, profiles/r2b)
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    last = atomicAdd(&m.ctr[3], 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
+  // (only thread 0 takes part: the other warps retire right away instead of waiting at a block barrier for thread 0's
+  // fence + atomic round trip -- 25 % of the kernel's stall samples in profiles/r2d)
+  if (threadIdx.x != 0) return;
+  __threadfence();
+  const bool last = atomicAdd(&m.ctr[3], 1) == (int)gridDim.x - 1;
+  if (last) {
     __threadfence();
     const long long rows = stats[1];
     if (user_stats) {

@@ -456,3 +456,44 @@ def test_host_buffer_call_matches_device_call(model, dev):
     with pytest.raises(RuntimeError):       # a frame larger than the map's max_points fails loudly
         big = torch.zeros((4096, 4096), dtype=torch.int16).pin_memory()
         model.fuse_depth_frame_host(vb, big, K, T, spec.max_depth)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tc16"])
+@pytest.mark.parametrize("hw", [(45, 70), (8, 32), (61, 33), (1, 1)])
+def test_ragged_frame_sizes_vs_oracle(model, tcnn_params, dev, mode, hw):
+    """Frame sizes that are not multiples of the prepass' 32 x 8 pixel tiles (partial tiles, replicate padding at the
+    image border inside a tile, a single pixel): fused depth path vs the oracle, ids / weights exact."""
+    from bnv_fusion_b200 import config
+    config.set_mlp_mode(mode)
+    H, W = hw
+    spec = synth.stream_spec("parity64")
+    grid = O.Grid.from_dimensions(spec.dimensions, spec.voxel_size)
+    vol = _volume(spec, dev, pool_capacity=1 << 16)
+    vm = O.VoxelMap(grid)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    n_total = 0
+    for fi in range(3):
+        d, K, T = synth.make_frame(spec, fi, seed=9)
+        d = np.ascontiguousarray(d[10:10 + H, 5:5 + W])
+        K = K.copy()
+        K[0, 2] -= 5
+        K[1, 2] -= 10
+        model.fuse_depth_frame(vol, _depth_to_dev(d, dev), K, T, spec.max_depth, stats=stats)
+        depth, mask = O.load_depth_u16(d, spec.max_depth)
+        feats, counts, flat, coords, _, _ = O.encode_pointcloud(O.backproject(depth, mask, K, T), grid, tcnn_params["encoder"], 8)
+        if flat is not None:
+            O.integrate(vm, flat, feats, counts)
+            n_total += len(flat)
+        st = stats.tolist()
+        assert st[0] == int(mask.sum()) and st[3] == (0 if flat is None else len(flat))
+    vol.check_status()
+    flat, feats, w, h = _map_sorted(vol)
+    rflat = np.sort(np.fromiter(vm.index.keys(), dtype=np.int64)) if len(vm) else np.zeros(0, np.int64)
+    assert np.array_equal(flat, rflat)
+    if len(flat):
+        rfeats, rw, _, _ = vm.query(flat)
+        np.testing.assert_allclose(w, rw, atol=1e-6, rtol=0)
+        np.testing.assert_allclose(feats, rfeats, atol=FEAT_ATOL if mode == "fp32" else 5e-3, rtol=0)
+    if hw == (45, 70):
+        assert len(flat) > 300
+    config.set_mlp_mode("tc16")
