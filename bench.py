@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """bench.py -- BNV-Fusion per-frame dense hot path on B200.
 
-A "step" is one pass of the hot path over one 640x480 synthetic depth frame of the `lounge`
-workload (BASELINE.json configs[1] shape: K = (525,525,319.5,239.5), 1 cm voxels, 5.1 m cube ->
-512^3 sparse grid): back-projection -> 8-neighbour expansion + encoder MLP + per-voxel scatter-mean
--> running-average integration into the voxel map (NeuralMap.integrate's local-fusion half,
-/root/reference/src/run_e2e.py:78-98).
+A "step" is one pass of the hot path over one batch of `--frame-batch` (default 7) 640x480 synthetic
+depth frames of the `lounge` workload (BASELINE.json configs[1] shape: K = (525,525,319.5,239.5), 1 cm
+voxels, 5.1 m cube -> 512^3 sparse grid): back-projection -> 8-neighbour expansion + encoder MLP +
+per-voxel scatter-mean -> running-average integration into the voxel map (NeuralMap.integrate's
+local-fusion half, /root/reference/src/run_e2e.py:78-98), through ONE bnv_fuse_frames call (the map ends
+up exactly as after one call per frame; tests/test_gpu_batch.py).  `--frame-batch 1` times the one-call-
+per-frame form; at N = 1 its numbers are also reported under "single_frame_calls".
 
   value      frames/s, depth frames resident in HBM, CUDA-event time per step, L2 flushed between
              steps (cold-cache, conservative);  `value_warm` = same steps back to back, no flush
@@ -206,18 +208,27 @@ def run_reference(args):
     }))
 
 
-def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick_log2, exchange, n_frames=8):
+def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick_log2, exchange, n_frames=8, batch=1):
     """N > 1 only: every rank fuses the first `n_frames` frames into a fresh tile-sharded map; rank 0 fuses the same
     frames into an UNSHARDED map and compares it with the union of the ranks' owned voxels: keys and fusion weights
     bit-exact, features <= 5e-5 (fp32 summation order), the 27 meshlize samples of every owned voxel (decoded on
     its owner from halo copies of foreign corners) <= 1e-4.  Returns the dict printed as "shard_parity"."""
     from bnv_fusion_b200.volume import SparseVolume
     from bnv_fusion_b200.dist import TileShardedFusion
-    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
+    if batch > 1:
+        n_frames = min(len(frames), 2 * batch)          # two batches through the sharded bnv_fuse_frames path
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21,
+                       frame_batch=batch if batch > 1 else 0)
     sh = TileShardedFusion(vol, model, rank, world, brick_log2=brick_log2, exchange=exchange, exchange_every=5)
     devf = [torch.from_numpy(frames[i][0].view(np.int16).copy()).to(dev).view(torch.uint16) for i in range(n_frames)]
-    for i in range(n_frames):
-        sh.fuse_depth_frame(devf[i], frames[i][1], frames[i][2], spec.max_depth)
+    if batch > 1:
+        for b0 in range(0, n_frames, batch):
+            ids = list(range(b0, min(b0 + batch, n_frames)))
+            sh.fuse_depth_frames([devf[i] for i in ids], np.stack([frames[i][1] for i in ids]),
+                                 np.stack([frames[i][2] for i in ids]), spec.max_depth)
+    else:
+        for i in range(n_frames):
+            sh.fuse_depth_frame(devf[i], frames[i][1], frames[i][2], spec.max_depth)
     vol.check_status()
     vol.to_tensor()
     vol.weights += 8.0
@@ -251,7 +262,7 @@ def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick
         rflat = rc[:, 0] * (n[1] * n[2]) + rc[:, 1] * n[2] + rc[:, 2]
         order = torch.argsort(rflat)
         keys_equal = got.shape[0] == rflat.shape[0] and bool((got[:, 0].long() == rflat[order]).all())
-        out = {"frames": n_frames, "voxels": int(rflat.shape[0]), "owned_per_rank": [int(v) for v in sizes.tolist()],
+        out = {"frames": n_frames, "frame_batch": batch, "voxels": int(rflat.shape[0]), "owned_per_rank": [int(v) for v in sizes.tolist()],
                "keys_equal": keys_equal, "weights_equal": False, "max_dfeat": None, "max_dsdf": None}
         if keys_equal:
             out["weights_equal"] = bool((got[:, 1].float() == ref.weights[order, 0]).all())
@@ -261,6 +272,49 @@ def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick
         del ref
     del vol
     return out
+
+
+def single_frame_calls(torch, model, spec, frames, devf, host, dev, flush, steps):
+    """The one-call-per-frame form (bnv_fuse_frame / bnv_fuse_frame_host, what an unchanged run_e2e.py loop issues) on a
+    map of its own with the single-frame table layout: cold device-resident frames/s and host-buffer frames/s."""
+    from bnv_fusion_b200.volume import SparseVolume
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+    n = len(frames)
+    for i in range(5):
+        model.fuse_depth_frame(vol, devf[i % n], frames[i % n][1], frames[i % n][2], spec.max_depth, stats=stats)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(steps):
+        j = (5 + i) % n
+        flush.zero_()
+        ev[i][0].record()
+        model.fuse_depth_frame(vol, devf[j], frames[j][1], frames[j][2], spec.max_depth, stats=stats)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    cold_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    def e2e(i):
+        j = i % n
+        model.fuse_depth_frame_host(vol, host[j], frames[j][1], frames[j][2], spec.max_depth, stats_host=stats_host,
+                                    next_depth_mm_host=host[(j + 1) % n])
+        torch.cuda.current_stream().synchronize()
+    for i in range(3):
+        e2e(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        e2e(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / steps
+    vol.check_status()
+    del vol
+    return {"value": 1e3 / cold_ms, "unit": "frames/s", "ms_per_frame": cold_ms, "e2e": 1e3 / e2e_ms,
+            "what": "one bnv_fuse_frame call per frame (an unchanged run_e2e.py loop): cold L2, device-resident frames; "
+                    "e2e = bnv_fuse_frame_host per frame with a host sync after every frame"}
 
 
 # --------------------------------------------------------------------------------------------- #
@@ -296,7 +350,8 @@ def run_b200(args):
     model.load_state_dict({"pointnet_backbone.model.params": torch.from_numpy(p["encoder"]),
                            "nerf.model.params": torch.from_numpy(p["decoder"])})
     model.eval(); model.cuda(); model.freeze()
-    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    B = max(1, int(args.frame_batch))               # frames per step (one bnv_fuse_frames call); 1: one call per frame
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, frame_batch=B if B > 1 else 0)
     shard = None
     if world > 1:
         from bnv_fusion_b200.dist import TileShardedFusion
@@ -305,26 +360,27 @@ def run_b200(args):
     H, W = spec.height, spec.width
     host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
     devf = [h.to(dev).view(torch.uint16) for h in host]
-    stage = torch.empty((H, W), dtype=torch.int16, device=dev)
+    Ks_all, Ts_all = np.stack([K for _, K, _ in frames]), np.stack([T for _, _, T in frames])
+    stage = torch.empty((B, H, W), dtype=torch.int16, device=dev)
+
+    def ids_of(i):                                   # the frames of step i
+        return [(i * B + j) % N_FRAMES for j in range(B)]
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def fuse(depth, K, T):
-        if shard is not None:      # tile shard: fuse own rows + ONE all-gather of boundary voxels
-            shard.fuse_depth_frame(depth, K, T, spec.max_depth, stats=stats)
-        else:
-            model.fuse_depth_frame(vol, depth, K, T, spec.max_depth, stats=stats)
+    target = shard if shard is not None else model   # tile shard: fuse own rows; boundary voxels go out once per epoch
+    pre = () if shard is not None else (vol,)
 
-    def step(i, from_host=False):
-        _, K, T = frames[i % N_FRAMES]
-        if from_host:
-            stage.copy_(host[i % N_FRAMES], non_blocking=True)
-            fuse(stage.view(torch.uint16), K, T)
-            stats_host.copy_(stats, non_blocking=True)
-            torch.cuda.current_stream().synchronize()          # the user reads the frame's result
+    def fuse(depths, ids):
+        if B == 1:
+            target.fuse_depth_frame(*pre, depths[0], Ks_all[ids[0]], Ts_all[ids[0]], spec.max_depth, stats=stats)
         else:
-            fuse(devf[i % N_FRAMES], K, T)
+            target.fuse_depth_frames(*pre, depths, Ks_all[ids], Ts_all[ids], spec.max_depth, stats=stats)
+
+    def step(i):
+        ids = ids_of(i)
+        fuse([devf[j] for j in ids], ids)
 
     def barrier():
         torch.cuda.synchronize()
@@ -379,13 +435,18 @@ def run_b200(args):
     # ---- end to end through the public API / C ABI with HOST buffers ----------------------------
     # every step: pinned uint16 depth -> H2D -> fuse -> D2H of the frame statistics -> host sync
     # (bnv_fuse_frame_host, one library call per frame; the tile shard adds its boundary exchange on the side stream)
+    def fuse_host(i, stats_to):
+        ids, nxt = ids_of(i), ids_of(i + 1)
+        if B == 1:
+            target.fuse_depth_frame_host(*pre, host[ids[0]], Ks_all[ids[0]], Ts_all[ids[0]], spec.max_depth, stats_host=stats_to,
+                                         next_depth_mm_host=host[nxt[0]])    # prefetch hint
+        else:
+            target.fuse_depth_frames_host(*pre, [host[j] for j in ids], Ks_all[ids], Ts_all[ids], spec.max_depth,
+                                          stats_host=stats_to, next_depths_mm_host=[host[j] for j in nxt])
+
     def step_e2e(i):
-        _, K, T = frames[i % N_FRAMES]
-        target = shard if shard is not None else model
-        args_ = () if shard is not None else (vol,)
-        target.fuse_depth_frame_host(*args_, host[i % N_FRAMES], K, T, spec.max_depth, stats_host=stats_host,
-                                     next_depth_mm_host=host[(i + 1) % N_FRAMES])    # prefetch hint
-        torch.cuda.current_stream().synchronize()          # the user reads the frame's result
+        fuse_host(i, stats_host)
+        torch.cuda.current_stream().synchronize()          # the user reads the step's result
 
     for i in range(3):
         step_e2e(i)
@@ -403,13 +464,8 @@ def run_b200(args):
     done2 = [torch.cuda.Event(), torch.cuda.Event()]
 
     def run_pipelined(first, count):
-        target = shard if shard is not None else model
-        args_ = () if shard is not None else (vol,)
         for j in range(count):
-            i = first + j
-            _, K, T = frames[i % N_FRAMES]
-            target.fuse_depth_frame_host(*args_, host[i % N_FRAMES], K, T, spec.max_depth, stats_host=stats2[j & 1],
-                                         next_depth_mm_host=host[(i + 1) % N_FRAMES])
+            fuse_host(first + j, stats2[j & 1])
             done2[j & 1].record()
             if j > 0:
                 done2[(j - 1) & 1].synchronize()           # the user reads frame i - 1's result while frame i runs
@@ -432,10 +488,12 @@ def run_b200(args):
     mn, mx, _ = get_world_range(spec.dimensions, 0.025)               # run_e2e.py:62-71: fixed 2.5 cm
     tsdf = TSDFVolume(np.stack([mn, mx], 1), 0.025, device=dev, verbose=False)
     def step_local(i):
-        _, K, T = frames[i % N_FRAMES]
-        stage.copy_(host[i % N_FRAMES], non_blocking=True)
-        fuse(stage.view(torch.uint16), K, T)
-        tsdf.integrate(None, stage.view(torch.uint16), K, T, 1.0)
+        ids = ids_of(i)
+        for b, j in enumerate(ids):
+            stage[b].copy_(host[j], non_blocking=True)
+        fuse([stage[b].view(torch.uint16) for b in range(B)], ids)
+        for b, j in enumerate(ids):
+            tsdf.integrate(None, stage[b].view(torch.uint16), Ks_all[j], Ts_all[j], 1.0)
         stats_host.copy_(stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     for i in range(3):
@@ -499,7 +557,7 @@ def run_b200(args):
 
     parity = None
     if world > 1 and not args.no_parity:
-        parity = shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, args.brick_log2, args.exchange)
+        parity = shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, args.brick_log2, args.exchange, batch=B)
     n_q_job, dec_ms_job = n_q, dec_ms
     if world > 1:      # whole-job decode: every rank decodes its own voxels; halo copies do not count
         own = int(shard.owned_rows().sum())
@@ -513,7 +571,10 @@ def run_b200(args):
     rows_per_launch = rows_total / args.steps
     enc_tflops = ENC_FLOP_PER_ROW * rows_per_launch / (enc_avg * 1e-3) / 1e12
     pre_avg, fin_avg = float(np.mean(pre_ms)), float(np.mean(fin_ms))
-    scatter_bytes = 2 * H * W + 64 + touched_total / args.steps * 44 + kept_total / args.steps * 80
+    scatter_bytes = B * (2 * H * W + 64) + touched_total / args.steps * 44 + kept_total / args.steps * 80
+    single = None
+    if world == 1 and B > 1:
+        single = single_frame_calls(torch, model, spec, frames, devf, host, dev, flush, args.steps)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         fps, dt = cpu_port(spec, frames, 2)
@@ -522,26 +583,29 @@ def run_b200(args):
                "tsdf": ref_tsdf(spec, frames)}
     if rank == 0:
         out = {
-            "metric": "fusion_frames_per_sec", "value": 1e3 / ms, "unit": "frames/s", "n_gpus": world,
+            "metric": "fusion_frames_per_sec", "value": 1e3 * B / ms, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD_DESC, "frames": N_FRAMES, "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
+            "config": {"workload": WORKLOAD_DESC, "frames": N_FRAMES, "frames_per_step": B,
+                       "step": ("one bnv_fuse_frames call over %d frames (map identical to one call per frame)" % B) if B > 1
+                               else "one bnv_fuse_frame call",
+                       "mlp": config.mlp_mode_name(), "l2": "flushed between timed steps (256 MB write)",
                        "parallelism": "1 GPU" if world == 1 else
                        f"tile shard over {world} GPUs, 3-D checkerboard of {1 << args.brick_log2}-voxel bricks, " +
                        (f"one all-gather of boundary voxels per {args.exchange_every} frames" if args.exchange == "nccl"
                         else f"peer-memory boundary routing every {args.exchange_every} frames")},
-            "value_warm": 1e3 / warm_ms,
+            "value_warm": 1e3 * B / warm_ms,
             "ms_per_step_with_kernel_events": staged_ms,
-            "e2e": {"value": 1e3 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": H * W * 2 + 100,
+            "e2e": {"value": 1e3 * B / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": B * (H * W * 2 + 100),
                     "d2h_bytes_per_step": 32,
-                    "what": "bnv_fuse_frame_host per frame: pinned uint16 depth -> H2D (the next frame's copy is hinted and "
-                            "overlaps this frame's kernels) -> fuse -> D2H frame statistics, then a host sync (the user reads "
-                            "the result of every frame)"},
-            "e2e_results_one_frame_behind": {"value": 1e3 / e2e_pipe_ms, "unit": "frames/s",
-                                             "what": "same call and copies per frame as e2e, but frame i is enqueued before the host "
-                                                     "waits for frame i - 1's statistics (every frame's statistics are still read)"},
-            "local_scope": {"value": 1e3 / local_ms, "unit": "frames/s", "tsdf_dims": tsdf_dims,
+                    "what": "bnv_fuse_frame(s)_host per step: pinned uint16 depth frames -> H2D (the next step's copies are hinted "
+                            "and overlap this step's kernels) -> fuse -> D2H statistics, then a host sync (the user reads "
+                            "the result of every step)"},
+            "e2e_results_one_frame_behind": {"value": 1e3 * B / e2e_pipe_ms, "unit": "frames/s",
+                                             "what": "same call and copies per step as e2e, but step i is enqueued before the host "
+                                                     "waits for step i - 1's statistics (every step's statistics are still read)"},
+            "local_scope": {"value": 1e3 * B / local_ms, "unit": "frames/s", "tsdf_dims": tsdf_dims,
                             "what": "reference 'local' timer scope (run_e2e.py:250-252): neural fusion + coarse TSDF "
                                     "integration at 2.5 cm, host depth in, frame stats out"},
             "gpu_launches": int(launches),
@@ -588,6 +652,8 @@ def run_b200(args):
                                                 "traffic": traffic("decode_ws_kernel" if config.mlp_mode_name() == "tc16" else "decode_simt_kernel")}}},
             "cpu_baseline": cpu,
         }
+        if single is not None:
+            out["single_frame_calls"] = single
         if parity is not None:
             out["shard_parity"] = parity
         print(json.dumps(out))
@@ -719,7 +785,9 @@ def run_sustained(args):
     model.load_state_dict({"pointnet_backbone.model.params": torch.from_numpy(p["encoder"]),
                            "nerf.model.params": torch.from_numpy(p["decoder"])})
     model.eval(); model.cuda(); model.freeze()
-    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev)
+    B = max(1, int(args.frame_batch))
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, frame_batch=B if B > 1 else 0)
+    Ks_all, Ts_all = np.stack([K for _, K, _ in frames]), np.stack([T for _, _, T in frames])
     target, pre = model, (vol,)
     if world > 1:
         from bnv_fusion_b200.dist import TileShardedFusion
@@ -728,10 +796,14 @@ def run_sustained(args):
     host = [torch.from_numpy(d.view(np.int16).copy()).pin_memory() for d, _, _ in frames]
     stats_host = torch.zeros(4, dtype=torch.int64).pin_memory()
 
-    def one(i):
-        _, K, T = frames[i % n_src]
-        target.fuse_depth_frame_host(*pre, host[i % n_src], K, T, spec.max_depth, stats_host=stats_host,
-                                     next_depth_mm_host=host[(i + 1) % n_src])
+    def one(i):                                      # step i: B frames in, their statistics out, host sync
+        ids, nxt = [(i * B + j) % n_src for j in range(B)], [((i + 1) * B + j) % n_src for j in range(B)]
+        if B == 1:
+            target.fuse_depth_frame_host(*pre, host[ids[0]], Ks_all[ids[0]], Ts_all[ids[0]], spec.max_depth, stats_host=stats_host,
+                                         next_depth_mm_host=host[nxt[0]])
+        else:
+            target.fuse_depth_frames_host(*pre, [host[j] for j in ids], Ks_all[ids], Ts_all[ids], spec.max_depth,
+                                          stats_host=stats_host, next_depths_mm_host=[host[j] for j in nxt])
         torch.cuda.current_stream().synchronize()
 
     for i in range(max(args.warmup, 5)):
@@ -739,18 +811,20 @@ def run_sustained(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    n = int(args.sustained)
+    per_mark = max(1, 100 // B)                      # steps per rate sample (~100 frames)
+    n_marks = max(1, int(args.sustained) // (per_mark * B))
+    n = n_marks * per_mark * B                       # frames actually run
     sampler.mark()
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n // 100 + 1)]
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(n_marks + 1)]
     marks[0].record()
-    for i in range(n):
+    for i in range(n_marks * per_mark):
         one(i)
-        if (i + 1) % 100 == 0:
-            marks[(i + 1) // 100].record()
+        if (i + 1) % per_mark == 0:
+            marks[(i + 1) // per_mark].record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     vol.check_status()
-    seg = [marks[j].elapsed_time(marks[j + 1]) for j in range(n // 100)]
+    seg = [marks[j].elapsed_time(marks[j + 1]) for j in range(n_marks)]
     total_ms = float(np.sum(seg))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -759,14 +833,15 @@ def run_sustained(args):
     n_vox = len(vol)
     if rank == 0:
         print(json.dumps({
-            "metric": "sustained_fusion_frames_per_sec", "value": (n // 100) * 100 / (total_ms * 1e-3), "unit": "frames/s",
-            "n_gpus": world, "steps": (n // 100) * 100, "warmup": max(args.warmup, 5), "higher_is_better": True, "data": "synthetic",
+            "metric": "sustained_fusion_frames_per_sec", "value": n / (total_ms * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": n // B, "frames": n, "frames_per_step": B, "warmup": max(args.warmup, 5),
+            "higher_is_better": True, "data": "synthetic",
             "dtype": "f16" if config.mlp_mode_name() == "tc16" else "f32",
-            "config": {"workload": WORKLOAD_DESC + f"; {n_src} distinct frames cycled, host buffers (H2D + stats D2H every frame)",
+            "config": {"workload": WORKLOAD_DESC + f"; {n_src} distinct frames cycled, host buffers (H2D + stats D2H + host sync every step of {B} frames)",
                        "parallelism": "1 GPU" if world == 1 else f"tile shard over {world} GPUs ({args.exchange} exchange every {args.exchange_every} frames)"},
-            "frames_per_sec_per_100_frames": [100.0 / (m * 1e-3) for m in seg],
+            "frames_per_sec_per_100_frames": [per_mark * B / (m * 1e-3) for m in seg],
             "clocks": clocks, "map_voxels_rank0": n_vox,
-            "e2e": {"value": (n // 100) * 100 / (total_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": spec.height * spec.width * 2 + 100,
+            "e2e": {"value": n / (total_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": B * (spec.height * spec.width * 2 + 100),
                     "d2h_bytes_per_step": 32}}))
     if world > 1:
         dist.destroy_process_group()
@@ -779,6 +854,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mlp", default=None, choices=[None, "fp32", "tc16"])
+    ap.add_argument("--frame-batch", type=int, default=7,
+                    help="frames per step = per bnv_fuse_frames call (1: one bnv_fuse_frame call per frame)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")

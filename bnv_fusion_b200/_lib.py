@@ -72,6 +72,10 @@ SIGNATURES = {
     "bnv_integrate": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "bnv_fuse_frame_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_fuse_frame": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "bnv_map_set_frame_batch": (C.c_int, [_P, C.c_int]),
+    "bnv_fuse_frames": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "bnv_fuse_frames_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P,
+                                       C.c_int, _P]),
     "bnv_fuse_points": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P]),
     "bnv_decode_sdf": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _I64, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "bnv_decode_sdf_backward": (C.c_int, [_P, _P, _I64, C.c_int, _P, _P, _I64, _P, C.c_int, _P, _P, _P]),

@@ -13,6 +13,7 @@ constexpr int kFeat = 8;            // feature_vector_size (configs/model/fusion
 constexpr int kWidth = 64;          // n_neurons (src/models/tcnn_config.json:28)
 constexpr int32_t kEmpty = -1;      // slot-table sentinel
 constexpr double kFixScale = 1073741824.0;  // 2^30: fixed-point scale of the per-frame sums
+constexpr int kMaxBatch = 15;       // frames per bnv_fuse_frames call (16 table words per grid cell, one is the lock)
 
 // latched device-side status bits
 constexpr int kErrCapacity = 1;     // value pool or frame scratch full
@@ -65,15 +66,20 @@ struct MapDev {
   // row whose atomicAdd returns count 0 touched the voxel first -- high 32 bits = the voxel's dense scratch row,
   // allocated by that first row from ctr[1].  Scratch rows are therefore contiguous in first-touch order
   // (fkeys / fsum rows [0, n_touched)), finalize streams them and zeroes the table entries it visits.
-  unsigned long long* ftable;  // [n_vox]
+  //
+  // Frame batches (bnv_fuse_frames): every grid cell owns 2^fshift consecutive words -- one per frame of the batch plus
+  // the LAST one as the cell's finalize lock -- so the entries of a voxel that consecutive frames keep touching share
+  // a cache line.  fshift == 0 (default): one word per cell, single frames only.
+  unsigned long long* ftable;  // [n_vox << fshift]
+  int32_t fshift;
   unsigned long long* ftable_dummy;   // [1024] sink of the prepass' no-op atomics (lanes without a run to count)
-  int32_t* fkeys;       // [fcap] flat id of scratch row
+  int32_t* fkeys;       // [fcap] flat id of scratch row (a (frame, voxel) pair in a batch)
   long long* fsum;      // [fcap, 8] 2^30 fixed-point int64 sums (exact-parity mode: order-independent => deterministic);
                         // the tensor-core mode uses the same buffer as float [fcap, 8]
   float* prec;          // [max_points, 8] compacted in-bounds point records of the frame: voxel-space xyz, normal, pad
-  int32_t fcap;         // min(8 * max_points, n_vox)
+  int32_t fcap;         // min(8 * max_points, n_vox * max(1, frames per batch))
   // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter, [4] n point records,
-  // [5] n dirty shell voxels
+  // [5] n dirty shell voxels, [6] chunk counter of the batch finalize
   int32_t* ctr;
   // tile shard (nullable): voxels on the shell of their brick that were integrated since the last boundary exchange
   // are remembered once each (flag per pool slot + list of slots, counter ctr[5]); bnv_map_halo_pack turns the list
@@ -82,6 +88,11 @@ struct MapDev {
   int32_t* dirty_list;  // [dirty_cap]
   int32_t dirty_cap;
 };
+
+// table word of (grid cell, frame of the batch)
+__host__ __device__ inline unsigned long long* ft_entry(const MapDev& m, int32_t flat, int frame) {
+  return m.ftable + (((size_t)flat << m.fshift) + (size_t)frame);
+}
 
 __host__ __device__ inline int owner_of(const GeomDev& g, int x, int y, int z) {
   return ((x >> g.brick_log2) + (y >> g.brick_log2) + (z >> g.brick_log2)) % g.world;
@@ -113,6 +124,8 @@ __host__ __device__ inline bool rank_touches(const GeomDev& g, int x, int y, int
 struct bnv_map {
   bnv::MapDev d;
   int device;
+  int batch_cap;        // frames per bnv_fuse_frames call the per-frame table is laid out for (0: single frames only)
+  unsigned int batch_seq;   // sequence number of the last batch (the finalize lock value; never 0)
   // scratch for the sorted encode_points path (CUB temp storage + index arrays)
   void* cub_tmp;
   size_t cub_tmp_bytes;
@@ -127,8 +140,9 @@ struct bnv_map {
   uint16_t* depth_stage[2];
   cudaStream_t copy_stream;
   cudaEvent_t stage_ready[2], stage_free[2];
-  const void* prefetched;  // host pointer whose copy into depth_stage[stage_next] is in flight / done
-  size_t prefetched_bytes;
+  const void* prefetched[bnv::kMaxBatch];  // host frames whose copy into depth_stage[stage_next] is in flight / done
+  int n_prefetched;
+  size_t prefetched_bytes;   // per frame
   int stage_next;
   int64_t* user_stats;   // device int64[4] frame statistics of bnv_fuse_frame_host
   float* bp_pts;

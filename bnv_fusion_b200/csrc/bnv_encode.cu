@@ -66,12 +66,15 @@ __global__ void compact_pts_kernel(const float* __restrict__ pts, const int32_t*
 // ------------------------------------------------------------------------------------------- //
 constexpr int kPreThreads = kTileW * kTileH;   // 256: one 32 x 8 pixel tile (a warp = 32 pixels of one image row)
 
-// NP x 32 (key, run length) pairs of a warp: NP independent, unconditional 32-bit atomics per lane on the LOW word
-// of the table entries (the count) -- straight-line code, so that all NP round trips to L2 are in flight before the
-// first result is read.  Returns the mask of pairs whose voxel this lane touched first (count was 0).
+// The (key, run length) pairs of a warp, lane j takes pairs j, j + 32, ...: NP = ceil(n_runs / 32) independent 32-bit
+// atomics per lane on the LOW word of the table entries (the count).  The first NP - 1 groups are full: unconditional,
+// straight-line code, so that all round trips to L2 are in flight before the first result is read; only the last,
+// partial group is predicated.  (Padding the partial groups with no-op atomics on a dummy word, as this kernel first
+// did, cost more than the real ones: 1.8 M atomic sectors per frame, two thirds of them padding -- profiles/r2e.)
+// Returns the mask of pairs whose voxel this lane touched first (count was 0).
 template <int NP>
-__device__ __forceinline__ uint32_t claim_runs(const MapDev& m, const int2* __restrict__ runs, int n_runs, int lane,
-                                               unsigned int* dummy, int2 (&pr)[8]) {
+__device__ __forceinline__ uint32_t claim_runs(const MapDev& m, int frame, const int2* __restrict__ runs, int n_runs, int lane,
+                                               int2 (&pr)[8]) {
   unsigned int old[NP];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -79,14 +82,15 @@ __device__ __forceinline__ uint32_t claim_runs(const MapDev& m, const int2* __re
     pr[j] = (j < NP && i < n_runs) ? runs[i] : make_int2(-1, 0);
   }
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    unsigned int* addr = pr[j].x >= 0 ? reinterpret_cast<unsigned int*>(m.ftable + pr[j].x) : dummy;
-    old[j] = atomicAdd(addr, (unsigned int)pr[j].y);
-  }
+  for (int j = 0; j < NP - 1; ++j)
+    old[j] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[j].x, frame)), (unsigned int)pr[j].y);
+  old[NP - 1] = 1u;
+  if (pr[NP - 1].x >= 0)
+    old[NP - 1] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[NP - 1].x, frame)), (unsigned int)pr[NP - 1].y);
   uint32_t win = 0;
 #pragma unroll
   for (int j = 0; j < NP; ++j)
-    if (pr[j].x >= 0 && old[j] == 0u) win |= 1u << j;
+    if (old[j] == 0u) win |= 1u << j;
   return win;
 }
 
@@ -96,8 +100,10 @@ __device__ __forceinline__ uint32_t claim_none(int2 (&pr)[8]) {
   return 0;
 }
 
+// `frame` = position of the frame in its batch (0 for a single frame): selects the frame's word of every table entry
+// and tags the point records.
 template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
+__device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src, int frame, long long* __restrict__ stats, int dbg) {
   // dbg (tools/prepass_ablation.py only; 0 in production): 1 no claim atomics, 2 no global counter atomics,
   // 4 no back-projection (every pixel invalid), 8 no record / key stores, 16 no depth staging
   __shared__ FrameTile tile;
@@ -197,14 +203,21 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
     n_runs += __popc(real);
   }
   __syncwarp();
-  // ---- claim + count: lane j takes pairs j, j + 32, ...; a lane without a pair adds 0 to a private dummy word ----
-  unsigned int* dummy = reinterpret_cast<unsigned int*>(m.ftable_dummy + ((blockIdx.x * kPreThreads + tid) & 1023));
+  // ---- claim + count: lane j takes pairs j, j + 32, ... ----
   int2 pr[8];
   const int2* runs = s_runs[warp];
-  const uint32_t win = (dbg & 1)       ? claim_none(pr)
-                       : n_runs <= 64  ? claim_runs<2>(m, runs, n_runs, lane, dummy, pr)
-                       : n_runs <= 128 ? claim_runs<4>(m, runs, n_runs, lane, dummy, pr)
-                                       : claim_runs<8>(m, runs, n_runs, lane, dummy, pr);
+  uint32_t win;
+  switch ((dbg & 1) ? 0 : (n_runs + 31) >> 5) {                        // warp-uniform
+    case 1: win = claim_runs<1>(m, frame, runs, n_runs, lane, pr); break;
+    case 2: win = claim_runs<2>(m, frame, runs, n_runs, lane, pr); break;
+    case 3: win = claim_runs<3>(m, frame, runs, n_runs, lane, pr); break;
+    case 4: win = claim_runs<4>(m, frame, runs, n_runs, lane, pr); break;
+    case 5: win = claim_runs<5>(m, frame, runs, n_runs, lane, pr); break;
+    case 6: win = claim_runs<6>(m, frame, runs, n_runs, lane, pr); break;
+    case 7: win = claim_runs<7>(m, frame, runs, n_runs, lane, pr); break;
+    case 8: win = claim_runs<8>(m, frame, runs, n_runs, lane, pr); break;
+    default: win = claim_none(pr); break;
+  }
   // ---- first touchers allocate dense scratch rows; in-bounds points get a record slot ---------------------
   const int n_new = __popc(win);
   int incl = n_new;
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
   for (int j = 0; j < 8; ++j)
     if ((win >> j) & 1u) {
       // publish the dense row in the entry's high word (visible to the kernels that follow) and its key
-      reinterpret_cast<int32_t*>(m.ftable + pr[j].x)[1] = row;
+      reinterpret_cast<int32_t*>(ft_entry(m, pr[j].x, frame))[1] = row;
       m.fkeys[row] = pr[j].x;
       // finalize will look this voxel up in the persistent table two kernels from now: pull the line into L2
       asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + pr[j].x));
@@ -261,8 +274,25 @@ __global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, En
   if (keep && !(dbg & 8)) {
     float4* r4 = reinterpret_cast<float4*>(m.prec + (size_t)rec * 8);
     r4[0] = make_float4(c[0], c[1], c[2], p[3]);
-    r4[1] = make_float4(p[4], p[5], __int_as_float((int)own), __int_as_float(pix));
+    r4[1] = make_float4(p[4], p[5], __int_as_float((int)own),
+                        __int_as_float((int)(((uint32_t)pix & 0xffffffu) | ((uint32_t)frame << 24))));
   }
+}
+
+template <bool FROM_DEPTH>
+__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
+  prepass_body<FROM_DEPTH>(m, src, 0, stats, dbg);
+}
+
+// a batch of frames in one launch: blockIdx.y = frame, blockIdx.x = pixel tile
+__global__ void __launch_bounds__(kPreThreads, 5) frame_prepass_batch_kernel(MapDev m, FrameBatch fb, long long* __restrict__ stats, int dbg) {
+  const int frame = blockIdx.y;
+  EncSrc src;
+  src.depth = fb.depth[frame];
+  src.cam = fb.cam[frame];
+  src.pts6 = nullptr;
+  src.n_points = 0;
+  prepass_body<true>(m, src, frame, stats, dbg);
 }
 
 // ------------------------------------------------------------------------------------------- //
@@ -285,6 +315,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_rows_simt_kernel(MapDev m,
     const float4 a = __ldg(r4), b = __ldg(r4 + 1);
     const float c[3] = {a.x, a.y, a.z}, nrm[3] = {a.w, b.x, b.y};
     const uint32_t own = (uint32_t)__float_as_int(b.z);
+    const int frame = record_frame(b.w);
     float fl[3], ce[3];
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(kEncThreads) encode_rows_simt_kernel(MapDev m,
         x[3 + ax] = nrm[ax];
       }
       EncMlp::run(sW, sH, kEncThreads, x, y);
-      add_row_fixed(m, scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]), y);
+      add_row_fixed(m, scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2], frame), y);
     }
   }
 }
@@ -325,6 +356,17 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
   finalize_publish(m, integrated, n_touched, stats, user_stats, user_navg);
 }
 
+// the same for a batch of frames: the first of a voxel's (frame, voxel) scratch rows to arrive makes its 8-lane group
+// do all the voxel's frames
+template <int S, bool F32>
+__global__ void __launch_bounds__(256, S == 8 ? 4 : 2) finalize_batch_kernel(MapDev m, int min_pts, unsigned int seq, long long* __restrict__ stats,
+                                                             long long* __restrict__ user_stats, float* __restrict__ user_navg) {
+  grid_dependency_wait();                               // the encoder MLP kernel
+  const int n_touched = m.ctr[1];
+  const int integrated = finalize_batch_rows<S, F32>(m, min_pts, seq, n_touched);
+  finalize_publish(m, integrated, n_touched, stats, user_stats, user_navg);
+}
+
 // ---- sorted path (encode_pointcloud's return values) ----------------------------------------
 __global__ void sort_prep_kernel(MapDev m, int n, int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +379,7 @@ __global__ void sort_flag_kernel(MapDev m, int n, const int32_t* __restrict__ ke
                                  int32_t* __restrict__ flags) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  flags[t] = ft_count(m.ftable[keys[t]]) >= min_pts ? 1 : 0;
+  flags[t] = ft_count(*ft_entry(m, keys[t], 0)) >= min_pts ? 1 : 0;
 }
 
 __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ keys, const int32_t* __restrict__ rows,
@@ -350,7 +392,7 @@ __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ ke
   if (t >= n) return;
   const int32_t row = rows[t];
   const int32_t key = keys[t];
-  const int32_t cnt = ft_count(m.ftable[key]);
+  const int32_t cnt = ft_count(*ft_entry(m, key, 0));
   const float mean = scratch_mean(m, row, j, cnt, f32acc);
   scratch_clear(m, row, j, f32acc);
   if (flags[t]) {
@@ -372,7 +414,7 @@ __global__ void sort_emit_kernel(MapDev m, int n, const int32_t* __restrict__ ke
     }
   }
   __syncwarp(0xFFu << ((threadIdx.x & 31) & ~7));
-  if (j == 0) m.ftable[key] = 0ull;
+  if (j == 0) *ft_entry(m, key, 0) = 0ull;
 }
 
 __global__ void sort_publish_kernel(MapDev m, int n, const int32_t* __restrict__ flags, const int32_t* __restrict__ scan,
@@ -473,11 +515,34 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 
 static int g_prepass_debug = 0;      // profiling ablations only (bnv_debug_prepass, not part of the ABI header)
+
+static int check_encoder(const bnv_mlp_t* enc, int mode) {
+  if (!enc || enc->n_in != 6 || enc->n_out != 8) { set_error("encode: encoder MLP must be 6 -> 8"); return BNV_E_ARG; }
+  if (mode != BNV_MLP_FP32 && mode != BNV_MLP_TC16) { set_error("encode: unknown MLP mode %d", mode); return BNV_E_ARG; }
+  return BNV_OK;
+}
+
+// kernel 2 of the frame: the encoder MLP over the point records the prepass wrote (at most `max_records`)
+static int launch_encode_rows(bnv_map_t* map, int64_t max_records, const bnv_mlp_t* enc, int mode, cudaStream_t s) {
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[3], s));
+  if (mode == BNV_MLP_TC16) return bnv_internal_encode_tc(map, max_records, enc, s);
+  static bool attr[64] = {false};            // cudaFuncSetAttribute is per device
+  if (!attr[map->device & 63]) {
+    BNV_CUDA(cudaFuncSetAttribute(encode_rows_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem));
+    attr[map->device & 63] = true;
+  }
+  const int64_t blocks = (max_records + kEncThreads - 1) / kEncThreads;
+  BNV_CUDA(launch_pdl(encode_rows_simt_kernel, dim3((unsigned)(blocks < 148 * 2 ? blocks : 148 * 2)), dim3(kEncThreads),
+                      kEncSmem, s, map->d, bnv_internal_simt_weights(enc)));
+  BNV_LAUNCH_CHECK("encode_rows_simt_kernel");
+  return BNV_OK;
+}
+
 // kernels 1 + 2 of the frame: prepass over `n_threads` pixels / points, then the encoder MLP over the records
 static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int64_t n_threads,
                          const bnv_mlp_t* enc, int mode, cudaStream_t s) {
-  if (!enc || enc->n_in != 6 || enc->n_out != 8) { set_error("encode: encoder MLP must be 6 -> 8"); return BNV_E_ARG; }
-  if (mode != BNV_MLP_FP32 && mode != BNV_MLP_TC16) { set_error("encode: unknown MLP mode %d", mode); return BNV_E_ARG; }
+  int rc = check_encoder(enc, mode);
+  if (rc) return rc;
   if (n_threads > map->max_points) {
     set_error("encode: %lld points exceed the map's max_points %lld", (long long)n_threads, (long long)map->max_points);
     return BNV_E_CAPACITY;
@@ -492,18 +557,7 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
                         dim3(kPreThreads), 0, s, map->d, src, (long long*)map->stats, g_prepass_debug));
   }
   BNV_LAUNCH_CHECK("frame_prepass_kernel");
-  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[3], s));
-  if (mode == BNV_MLP_TC16) return bnv_internal_encode_tc(map, n_threads, enc, s);
-  static bool attr[64] = {false};            // cudaFuncSetAttribute is per device
-  if (!attr[map->device & 63]) {
-    BNV_CUDA(cudaFuncSetAttribute(encode_rows_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem));
-    attr[map->device & 63] = true;
-  }
-  const int64_t blocks = (n_threads + kEncThreads - 1) / kEncThreads;
-  BNV_CUDA(launch_pdl(encode_rows_simt_kernel, dim3((unsigned)(blocks < 148 * 2 ? blocks : 148 * 2)), dim3(kEncThreads),
-                      kEncSmem, s, map->d, bnv_internal_simt_weights(enc)));
-  BNV_LAUNCH_CHECK("encode_rows_simt_kernel");
-  return BNV_OK;
+  return launch_encode_rows(map, n_threads, enc, mode, s);
 }
 
 static int launch_finalize(bnv_map_t* map, int min_pts, int mode, int64_t* frame_stats, float* navg, cudaStream_t s) {
@@ -556,6 +610,51 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth, int H, int W, const fl
   return rc;
 }
 
+// host frames -> the map's staging buffer `cur` (frames back to back), unless the copy stream already brought exactly
+// these frames there (prefetch hint of the previous call)
+static int stage_frames(bnv_map_t* map, const uint16_t* const* depth_host, int n, size_t bytes, cudaStream_t s) {
+  if (!map->copy_stream) {                       // first use: copy stream + buffer events
+    BNV_CUDA(cudaStreamCreateWithFlags(&map->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_ready[i], cudaEventDisableTiming));
+      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_free[i], cudaEventDisableTiming));
+      BNV_CUDA(cudaEventRecord(map->stage_free[i], s));
+    }
+  }
+  const int cur = map->stage_next;
+  // a prefetch hinted at the previous call targets depth_stage[cur]: whether or not it is what is passed now,
+  // nothing on `s` may read or overwrite that buffer before the copy stream's write has landed
+  if (map->n_prefetched) BNV_CUDA(cudaStreamWaitEvent(s, map->stage_ready[cur], 0));
+  bool hit = map->n_prefetched == n && map->prefetched_bytes == bytes;
+  for (int i = 0; hit && i < n; ++i) hit = map->prefetched[i] == depth_host[i];
+  if (!hit)
+    for (int i = 0; i < n; ++i)
+      BNV_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(map->depth_stage[cur]) + (size_t)i * bytes, depth_host[i], bytes,
+                               cudaMemcpyHostToDevice, s));
+  return BNV_OK;
+}
+
+// after the frames' kernels are enqueued: release the staging buffer, start the hinted copy into the other one
+static int stage_next_frames(bnv_map_t* map, const uint16_t* const* next_host, int n, size_t bytes, cudaStream_t s) {
+  const int cur = map->stage_next;
+  BNV_CUDA(cudaEventRecord(map->stage_free[cur], s));                  // this staging buffer's readers are done
+  map->n_prefetched = 0;
+  map->stage_next = cur ^ 1;
+  if (next_host && n > 0) {
+    const int nxt = cur ^ 1;
+    BNV_CUDA(cudaStreamWaitEvent(map->copy_stream, map->stage_free[nxt], 0));
+    for (int i = 0; i < n; ++i) {
+      BNV_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(map->depth_stage[nxt]) + (size_t)i * bytes, next_host[i], bytes,
+                               cudaMemcpyHostToDevice, map->copy_stream));
+      map->prefetched[i] = next_host[i];
+    }
+    BNV_CUDA(cudaEventRecord(map->stage_ready[nxt], map->copy_stream));
+    map->n_prefetched = n;
+    map->prefetched_bytes = bytes;
+  }
+  return BNV_OK;
+}
+
 int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_host, int H, int W, const float* K, const float* T,
                         double max_depth, const bnv_mlp_t* enc, int min_pts, int mode, int64_t* frame_stats_host,
                         const uint16_t* next_depth_host, void* stream) {
@@ -566,37 +665,92 @@ int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_host, int H, int W
   }
   cudaStream_t s = (cudaStream_t)stream;
   const size_t bytes = (size_t)H * W * 2;
-  if (!map->copy_stream) {                       // first use: copy stream + buffer events
-    BNV_CUDA(cudaStreamCreateWithFlags(&map->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_ready[i], cudaEventDisableTiming));
-      BNV_CUDA(cudaEventCreateWithFlags(&map->stage_free[i], cudaEventDisableTiming));
-      BNV_CUDA(cudaEventRecord(map->stage_free[i], s));
-    }
-  }
-  const int cur = map->stage_next;
-  // a prefetch hinted at the previous call targets depth_stage[cur]: whether or not it is the frame passed now,
-  // nothing on `s` may read or overwrite that buffer before the copy stream's write has landed
-  if (map->prefetched) BNV_CUDA(cudaStreamWaitEvent(s, map->stage_ready[cur], 0));
-  if (!(map->prefetched == depth_host && map->prefetched_bytes == bytes))
-    BNV_CUDA(cudaMemcpyAsync(map->depth_stage[cur], depth_host, bytes, cudaMemcpyHostToDevice, s));
-  int rc = bnv_fuse_frame(map, map->depth_stage[cur], H, W, K, T, max_depth, enc, min_pts, mode,
-                          frame_stats_host ? map->user_stats : nullptr, nullptr, stream);
+  int rc = stage_frames(map, &depth_host, 1, bytes, s);
+  if (rc) return rc;
+  rc = bnv_fuse_frame(map, map->depth_stage[map->stage_next], H, W, K, T, max_depth, enc, min_pts, mode,
+                      frame_stats_host ? map->user_stats : nullptr, nullptr, stream);
   if (rc) return rc;
   if (frame_stats_host)
     BNV_CUDA(cudaMemcpyAsync(frame_stats_host, map->user_stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  BNV_CUDA(cudaEventRecord(map->stage_free[cur], s));                  // this staging buffer's readers are done
-  map->prefetched = nullptr;
-  map->stage_next = cur ^ 1;
-  if (next_depth_host) {
-    const int nxt = cur ^ 1;
-    BNV_CUDA(cudaStreamWaitEvent(map->copy_stream, map->stage_free[nxt], 0));
-    BNV_CUDA(cudaMemcpyAsync(map->depth_stage[nxt], next_depth_host, bytes, cudaMemcpyHostToDevice, map->copy_stream));
-    BNV_CUDA(cudaEventRecord(map->stage_ready[nxt], map->copy_stream));
-    map->prefetched = next_depth_host;
-    map->prefetched_bytes = bytes;
+  return stage_next_frames(map, &next_depth_host, next_depth_host ? 1 : 0, bytes, s);
+}
+
+// ---- frame batches ---------------------------------------------------------------------------------------------
+static int check_batch(bnv_map_t* map, int n_frames, int H, int W, const char* who) {
+  if (n_frames < 1 || H <= 0 || W <= 0) { set_error("%s: bad argument", who); return BNV_E_ARG; }
+  if (n_frames > map->batch_cap) {
+    set_error("%s: %d frames, but the map is laid out for batches of %d (bnv_map_set_frame_batch)", who, n_frames, map->batch_cap);
+    return BNV_E_CAPACITY;
+  }
+  if ((int64_t)H * W > (1 << 24) || (int64_t)n_frames * H * W > map->max_points) {
+    set_error("%s: %d frames of %d x %d pixels exceed the map's max_points %lld", who, n_frames, H, W, (long long)map->max_points);
+    return BNV_E_CAPACITY;
   }
   return BNV_OK;
+}
+
+int bnv_fuse_frames(bnv_map_t* map, const uint16_t* const* depth, int n_frames, int H, int W, const float* K, const float* T,
+                    double max_depth, const bnv_mlp_t* enc, int min_pts, int mode, int64_t* batch_stats, float* navg,
+                    void* stream) {
+  if (!map || !depth) { set_error("bnv_fuse_frames: null argument"); return BNV_E_ARG; }
+  int rc = check_batch(map, n_frames, H, W, "bnv_fuse_frames");
+  if (rc) return rc;
+  rc = check_encoder(enc, mode);
+  if (rc) return rc;
+  FrameBatch fb{};
+  for (int i = 0; i < n_frames; ++i) {
+    if (!depth[i]) { set_error("bnv_fuse_frames: null frame %d", i); return BNV_E_ARG; }
+    rc = make_camera(fb.cam[i], H, W, K ? K + 9 * i : nullptr, T ? T + 16 * i : nullptr, max_depth);
+    if (rc) return rc;
+    fb.depth[i] = depth[i];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
+  const unsigned tiles = (unsigned)(((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH));
+  BNV_CUDA(launch_pdl(frame_prepass_batch_kernel, dim3(tiles, (unsigned)n_frames), dim3(kPreThreads), 0, s, map->d, fb,
+                      (long long*)map->stats, g_prepass_debug));
+  BNV_LAUNCH_CHECK("frame_prepass_batch_kernel");
+  rc = launch_encode_rows(map, (int64_t)n_frames * H * W, enc, mode, s);
+  if (rc) return rc;
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
+  if (++map->batch_seq == 0u) map->batch_seq = 1u;     // 0 is the cleared lock word (a wrap after 2^32 batches)
+  {
+    const dim3 grid(148 * 4), block(256);
+    const bool f32 = mode == BNV_MLP_TC16, wide = map->d.fshift == 4;
+    auto kernel = wide ? (f32 ? finalize_batch_kernel<16, true> : finalize_batch_kernel<16, false>)
+                       : (f32 ? finalize_batch_kernel<8, true> : finalize_batch_kernel<8, false>);
+    BNV_CUDA(launch_pdl(kernel, grid, block, 0, s, map->d, min_pts, map->batch_seq, (long long*)map->stats,
+                        (long long*)batch_stats, navg));
+  }
+  BNV_LAUNCH_CHECK("finalize_batch_kernel");
+  if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[2], s));
+  return BNV_OK;
+}
+
+int bnv_fuse_frames_host(bnv_map_t* map, const uint16_t* const* depth_host, int n_frames, int H, int W, const float* K,
+                         const float* T, double max_depth, const bnv_mlp_t* enc, int min_pts, int mode,
+                         int64_t* batch_stats_host, const uint16_t* const* next_depth_host, int n_next, void* stream) {
+  if (!map || !depth_host) { set_error("bnv_fuse_frames_host: null argument"); return BNV_E_ARG; }
+  int rc = check_batch(map, n_frames, H, W, "bnv_fuse_frames_host");
+  if (rc) return rc;
+  if (n_next < 0 || n_next > map->batch_cap || (int64_t)n_next * H * W > map->max_points) {
+    set_error("bnv_fuse_frames_host: bad prefetch hint (%d frames)", n_next);
+    return BNV_E_ARG;
+  }
+  for (int i = 0; i < n_frames; ++i)
+    if (!depth_host[i]) { set_error("bnv_fuse_frames_host: null frame %d", i); return BNV_E_ARG; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)H * W * 2;
+  rc = stage_frames(map, depth_host, n_frames, bytes, s);
+  if (rc) return rc;
+  const uint16_t* dev[kMaxBatch];
+  for (int i = 0; i < n_frames; ++i) dev[i] = map->depth_stage[map->stage_next] + (size_t)i * H * W;
+  rc = bnv_fuse_frames(map, dev, n_frames, H, W, K, T, max_depth, enc, min_pts, mode,
+                       batch_stats_host ? map->user_stats : nullptr, nullptr, stream);
+  if (rc) return rc;
+  if (batch_stats_host)
+    BNV_CUDA(cudaMemcpyAsync(batch_stats_host, map->user_stats, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  return stage_next_frames(map, next_depth_host, next_depth_host ? n_next : 0, bytes, s);
 }
 
 int bnv_fuse_points(bnv_map_t* map, const float* pts6, int64_t n_points, const bnv_mlp_t* enc, int min_pts,

@@ -147,6 +147,12 @@ struct EncSrc {
   int64_t n_points;
 };
 
+// the frames of one bnv_fuse_frames call (a kernel parameter: 1.3 KB of the 4 KB parameter space)
+struct FrameBatch {
+  Camera cam[kMaxBatch];
+  const uint16_t* depth[kMaxBatch];
+};
+
 // Programmatic dependent launch (sm_90+): the frame's kernels are launched with programmatic stream serialization,
 // so a kernel's launch and prologue overlap the tail of the kernel before it; everything that depends on that
 // kernel's results comes after this wait (a no-op for a normally launched kernel).
@@ -156,9 +162,11 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 __device__ __forceinline__ int32_t ft_count(unsigned long long e) { return (int32_t)(e & 0xffffffffull); }
 __device__ __forceinline__ int32_t ft_row(unsigned long long e) { return (int32_t)(e >> 32); }
 // dense scratch row of a voxel touched this frame (valid in kernels after the prepass)
-__device__ __forceinline__ int32_t scratch_row_of(const MapDev& m, int32_t flat) {
-  return __ldg(reinterpret_cast<const int32_t*>(m.ftable + flat) + 1);
+__device__ __forceinline__ int32_t scratch_row_of(const MapDev& m, int32_t flat, int frame) {
+  return __ldg(reinterpret_cast<const int32_t*>(ft_entry(m, flat, frame)) + 1);
 }
+// point records (MapDev::prec) carry the frame's position in its batch in the top byte of their last word
+__device__ __forceinline__ int record_frame(float last_word) { return (int)((uint32_t)__float_as_int(last_word) >> 24); }
 
 // exact-parity mode: 2^30 fixed-point int64 sums (integer addition is associative => bit-reproducible means)
 __device__ __forceinline__ void add_row_fixed(const MapDev& m, int32_t row, const float (&y)[8]) {

@@ -374,6 +374,57 @@ int bnv_map_create(bnv_map_t** out, const bnv_geom_t* geom, int n_feats, int64_t
   return BNV_OK;
 }
 
+int bnv_map_set_frame_batch(bnv_map_t* m, int n_frames) {
+  if (!m || n_frames < 0 || n_frames > kMaxBatch) {
+    set_error("bnv_map_set_frame_batch: frames per batch must be in [0, %d]", kMaxBatch);
+    return BNV_E_ARG;
+  }
+  BNV_CUDA(cudaSetDevice(m->device));
+  BNV_CUDA(cudaDeviceSynchronize());             // no frame may be in flight while the per-frame table is replaced
+  MapDev& d = m->d;
+  const int shift = n_frames == 0 ? 0 : n_frames < 8 ? 3 : 4;
+  const int64_t pairs = d.g.n_vox * (n_frames > 1 ? n_frames : 1);       // (frame, voxel) pairs a call can touch
+  const int64_t fcap = m->max_points * 8 < pairs ? m->max_points * 8 : pairs;
+  if (shift != d.fshift) {
+    BNV_CUDA(cudaFree(d.ftable));
+    d.ftable = nullptr;
+    d.fshift = 0;
+    m->batch_cap = 0;
+    const size_t bytes = ((size_t)d.g.n_vox << shift) * 8;
+    cudaError_t e = cudaMalloc((void**)&d.ftable, bytes);
+    if (e != cudaSuccess) {                      // fall back to the single-frame layout so that the map stays usable
+      cudaGetLastError();
+      BNV_CUDA(cudaMalloc((void**)&d.ftable, (size_t)d.g.n_vox * 8));
+      BNV_CUDA(cudaMemset(d.ftable, 0, (size_t)d.g.n_vox * 8));
+      set_error("bnv_map_set_frame_batch: no memory for %zu bytes of per-frame table", bytes);
+      return BNV_E_ALLOC;
+    }
+    BNV_CUDA(cudaMemset(d.ftable, 0, bytes));
+    d.fshift = shift;
+    m->batch_seq = 0;
+  }
+  if (fcap > d.fcap) {                           // scratch rows for every (frame, voxel) pair of a batch
+    int32_t* fkeys = nullptr;
+    long long* fsum = nullptr;
+    cudaError_t e = cudaMalloc((void**)&fkeys, (size_t)fcap * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&fsum, (size_t)fcap * kFeat * 8);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      if (fkeys) cudaFree(fkeys);
+      set_error("bnv_map_set_frame_batch: no memory for %lld scratch rows", (long long)fcap);
+      return BNV_E_ALLOC;
+    }
+    BNV_CUDA(cudaMemset(fsum, 0, (size_t)fcap * kFeat * 8));
+    cudaFree(d.fkeys);
+    cudaFree(d.fsum);
+    d.fkeys = fkeys;
+    d.fsum = fsum;
+    d.fcap = (int32_t)fcap;
+  }
+  m->batch_cap = n_frames;
+  return BNV_OK;
+}
+
 int bnv_map_destroy(bnv_map_t* m) {
   if (!m) return BNV_OK;
   cudaSetDevice(m->device);

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_ws_kernel(MapDev m, const 
       // corners of this chain's unit range that this rank owns (the prepass stored the ownership mask)
       const uint32_t range = ((1u << k1) - 1u) & ~((1u << k0) - 1u);
       const uint32_t own = (idx < n_rec ? (uint32_t)__float_as_int(rb.z) : 0u) & range;
+      const int frame = record_frame(rb.w);               // position of the record's frame in its batch
       int32_t rows[8];                                    // dense scratch rows of the owned corners (8 reads in flight)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_ws_kernel(MapDev m, const 
         if ((own >> k) & 1u) {
           float nb[3];
           corner_of(k, fl, ce, nb);
-          rows[k] = scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2]);   // rule A5
+          rows[k] = scratch_row_of(m, (int)nb[0] * g.nyz + (int)nb[1] * g.n[2] + (int)nb[2], frame);   // rule A5
         }
       }
       // corners to run: all of [k0, k1) on one GPU; in the tile shard only those somebody in the warpgroup owns

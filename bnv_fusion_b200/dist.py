@@ -173,8 +173,17 @@ class TileShardedFusion:
                                          next_depth_mm_host=next_depth_mm_host)
         self._frame_done()
 
-    def _frame_done(self):
-        self._since += 1
+    def fuse_depth_frames(self, depths_mm, Ks, Ts_wc, max_depth=3.0, stats=None, navg=None):
+        self.model.fuse_depth_frames(self.volume, depths_mm, Ks, Ts_wc, max_depth, stats=stats, navg=navg)
+        self._frame_done(len(depths_mm))
+
+    def fuse_depth_frames_host(self, depths_mm_host, Ks, Ts_wc, max_depth=3.0, stats_host=None, next_depths_mm_host=None):
+        self.model.fuse_depth_frames_host(self.volume, depths_mm_host, Ks, Ts_wc, max_depth, stats_host=stats_host,
+                                          next_depths_mm_host=next_depths_mm_host)
+        self._frame_done(len(depths_mm_host))
+
+    def _frame_done(self, n=1):
+        self._since += n
         if self.world > 1 and self._since >= self.exchange_every:
             self.exchange_now()
 

@@ -290,6 +290,52 @@ class LitFusionPointNet(nn.Module):
                                                    C.c_void_p(next_depth_mm_host.data_ptr()) if next_depth_mm_host is not None else None,
                                                    volume._stream()), "bnv_fuse_frame_host")
 
+    # ---- frame batches: n frames through ONE pass of the three kernels (include/bnv_b200.h "frame batches") ----------
+    @staticmethod
+    def _batch_cameras(n, Ks, Ts):
+        K = np.asarray(Ks, np.float32)
+        K = np.broadcast_to(K.reshape(-1, 9), (n, 9)) if K.size == 9 else K.reshape(n, 9)
+        T = np.asarray(Ts, np.float32).reshape(n, 16)
+        return np.ascontiguousarray(K), np.ascontiguousarray(T)
+
+    def fuse_depth_frames(self, volume, depths_mm, Ks, Ts_wc, max_depth=3.0, stats=None, navg=None):
+        """Fuse a batch of depth frames: the map ends up exactly as after `fuse_depth_frame` on each of them in order
+        (the per-voxel running averages are applied in frame order by one thread per voxel).  depths_mm: sequence of
+        uint16 [H,W] CUDA tensors or one [n,H,W] tensor; Ks [3,3] (shared) or [n,3,3]; Ts_wc [n,4,4].  The volume must
+        have been laid out for batches: `SparseVolume(..., frame_batch=n)` or `volume.set_frame_batch(n)`.
+        stats (optional CUDA int64[4]) receives the frame statistics summed over the batch."""
+        frames = list(depths_mm)
+        n = len(frames)
+        H, W = frames[0].shape
+        for d in frames:
+            assert d.is_cuda and d.dtype in (torch.uint16, torch.int16) and tuple(d.shape) == (H, W) and d.is_contiguous()
+        K, T = self._batch_cameras(n, Ks, Ts_wc)
+        ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in frames])
+        _lib.check(volume._lib.bnv_fuse_frames(volume._handle, ptrs, n, H, W, _lib.ptr(K), _lib.ptr(T), float(max_depth),
+                                               self.pointnet_backbone._mlp_handle(), int(self.min_pts_in_grid),
+                                               config.mlp_mode(), _lib.ptr(stats), _lib.ptr(navg), volume._stream()),
+                   "bnv_fuse_frames")
+
+    def fuse_depth_frames_host(self, volume, depths_mm_host, Ks, Ts_wc, max_depth=3.0, stats_host=None,
+                               next_depths_mm_host=None):
+        """Host-buffer form of `fuse_depth_frames` (pinned CPU uint16/int16 [H,W] tensors), with the prefetch hint of
+        `fuse_depth_frame_host` for the frames of the next call."""
+        frames = list(depths_mm_host)
+        n = len(frames)
+        H, W = frames[0].shape
+        for d in frames:
+            assert not d.is_cuda and d.dtype in (torch.uint16, torch.int16) and tuple(d.shape) == (H, W) and d.is_contiguous()
+        K, T = self._batch_cameras(n, Ks, Ts_wc)
+        ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in frames])
+        nxt = list(next_depths_mm_host) if next_depths_mm_host is not None else []
+        nptrs = (C.c_void_p * max(1, len(nxt)))(*[d.data_ptr() for d in nxt])
+        _lib.check(volume._lib.bnv_fuse_frames_host(volume._handle, ptrs, n, H, W, _lib.ptr(K), _lib.ptr(T), float(max_depth),
+                                                    self.pointnet_backbone._mlp_handle(), int(self.min_pts_in_grid),
+                                                    config.mlp_mode(),
+                                                    C.c_void_p(stats_host.data_ptr()) if stats_host is not None else None,
+                                                    nptrs if nxt else None, len(nxt), volume._stream()),
+                   "bnv_fuse_frames_host")
+
     def fuse_points(self, volume, input_pts, stats=None, navg=None):
         pts = input_pts.reshape(-1, 6).detach().float().contiguous()
         _lib.check(volume._lib.bnv_fuse_points(volume._handle, _lib.ptr(pts), pts.shape[0],

@@ -93,7 +93,7 @@ class TriangleMesh:
 
 class SparseVolume:
     def __init__(self, n_feats, voxel_size, dimensions, min_pts_in_grid, capacity=100000,
-                 device="cuda:0", max_points=None, pool_capacity=None):
+                 device="cuda:0", max_points=None, pool_capacity=None, frame_batch=0):
         min_coords, max_coords, n_xyz = get_world_range(dimensions, voxel_size)
         self.device = device
         self.dimensions = dimensions
@@ -109,7 +109,9 @@ class SparseVolume:
         # The reference's `capacity` is only the hash map's INITIAL size (Open3D rehashes on
         # growth); the value pool here is sized once for HBM3e: 16 Mi voxels = 0.67 GB.
         self._pool = int(pool_capacity or max(int(capacity), config.DEFAULT_POOL_CAPACITY))
-        self._max_points = int(max_points or config.DEFAULT_MAX_POINTS)
+        # frame_batch > 0: per-frame scratch for `frame_batch` frames per LitFusionPointNet.fuse_depth_frames call
+        self._max_points = int(max_points or config.DEFAULT_MAX_POINTS * max(1, int(frame_batch)))
+        self.frame_batch = 0
         geom = _lib.Geom()
         bmin32 = torch.from_numpy(min_coords).float().numpy()
         bmax32 = torch.from_numpy(max_coords).float().numpy()
@@ -123,6 +125,8 @@ class SparseVolume:
             _lib.check(self._lib.bnv_map_create(C.byref(self._handle), C.byref(geom), int(n_feats),
                                                 self._pool, self._max_points, self._dev_index),
                        "bnv_map_create")
+        if frame_batch:
+            self.set_frame_batch(frame_batch)
         self.reset(capacity, _fresh=True)
         _REGISTRY[geometry_key(n_xyz, bmin32, voxel_size) + (self._dev_index,)] = self
 
@@ -131,6 +135,13 @@ class SparseVolume:
         self.n_frames = 0
         self.min_pts = 1000
         self.max_pts = 0
+
+    def set_frame_batch(self, n_frames):
+        """Lay the per-frame table out for batches of up to n_frames frames (0: single frames only).  The volume's
+        max_points must cover n_frames * H * W pixels.  Synchronises the device."""
+        with torch.cuda.device(self._dev_index):
+            _lib.check(self._lib.bnv_map_set_frame_batch(self._handle, int(n_frames)), "bnv_map_set_frame_batch")
+        self.frame_batch = int(n_frames)
 
     def __del__(self):
         try:

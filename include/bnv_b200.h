@@ -194,6 +194,32 @@ int bnv_fuse_frame(bnv_map_t* map, const uint16_t* depth_mm_dev, int H, int W, c
 int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_mm_host, int H, int W, const float* K_host,
                         const float* T_wc_host, double max_depth, const bnv_mlp_t* enc, int min_pts,
                         int mode, int64_t* frame_stats_host, const uint16_t* next_depth_mm_host, void* stream);
+/* ---- frame batches ----------------------------------------------------------------------------
+ * The reference's driver loop (src/run_e2e.py:229-252: `for frame in loader: neural_map.integrate(frame)`) fuses one
+ * frame per iteration.  Back-projection, encoding and the per-voxel means of a frame do not depend on the map, only
+ * the final running average (_update, local_point_fusion.py:647-651) does, and it only has to be applied per voxel
+ * in frame order.  bnv_fuse_frames therefore fuses n_frames depth frames in ONE pass of the three kernels -- the map
+ * ends up exactly as after n_frames bnv_fuse_frame calls in the same order (bit-identical in BNV_MLP_FP32 mode) --
+ * which amortises the kernels' fixed latencies over the batch (offline scenes, or a live stream that tolerates
+ * n_frames of delay).
+ *
+ * bnv_map_set_frame_batch lays the per-frame table out for batches of up to n_frames (<= 15) frames: 8 (n_frames < 8)
+ * or 16 table words per grid cell instead of 1; n_frames == 0 restores the single-frame layout.  The map must have
+ * been created with max_points >= n_frames * H * W.  Synchronises the device. */
+int bnv_map_set_frame_batch(bnv_map_t* map, int n_frames);
+/* depth_mm_dev: HOST array of n_frames device pointers ([H,W] uint16 each); K_host [n_frames,3,3], T_wc_host
+ * [n_frames,4,4] row-major fp32.  batch_stats_dev (nullable) int64[4] = the four bnv_fuse_frame statistics summed
+ * over the batch; navg_dev nullable. */
+int bnv_fuse_frames(bnv_map_t* map, const uint16_t* const* depth_mm_dev, int n_frames, int H, int W,
+                    const float* K_host, const float* T_wc_host, double max_depth, const bnv_mlp_t* enc,
+                    int min_pts, int mode, int64_t* batch_stats_dev, float* navg_dev, void* stream);
+/* bnv_fuse_frames with HOST frames (depth_mm_host: n_frames host pointers, pinned for asynchronous copies) and the
+ * prefetch hint of bnv_fuse_frame_host for the n_next frames of the next call (next_depth_mm_host nullable). */
+int bnv_fuse_frames_host(bnv_map_t* map, const uint16_t* const* depth_mm_host, int n_frames, int H, int W,
+                         const float* K_host, const float* T_wc_host, double max_depth, const bnv_mlp_t* enc,
+                         int min_pts, int mode, int64_t* batch_stats_host,
+                         const uint16_t* const* next_depth_mm_host, int n_next, void* stream);
+
 /* Same, starting from world-space points (frame['input_pts'], [n,6] fp32). */
 int bnv_fuse_points(bnv_map_t* map, const float* pts6_dev, int64_t n_points, const bnv_mlp_t* enc,
                     int min_pts, int mode, int64_t* frame_stats_dev, float* navg_dev, void* stream);
