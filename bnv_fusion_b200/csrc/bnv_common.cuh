@@ -13,12 +13,18 @@ constexpr int kFeat = 8;            // feature_vector_size (configs/model/fusion
 constexpr int kWidth = 64;          // n_neurons (src/models/tcnn_config.json:28)
 constexpr int32_t kEmpty = -1;      // slot-table sentinel
 constexpr double kFixScale = 1073741824.0;  // 2^30: fixed-point scale of the per-frame sums
-constexpr int kMaxBatch = 15;       // frames per bnv_fuse_frames call (16 table words per grid cell, one is the lock)
+constexpr int kMaxBatch = 7;        // frames per bnv_fuse_frames call (8 table words per grid cell, one is the lock)
 
 // latched device-side status bits
 constexpr int kErrCapacity = 1;     // value pool or frame scratch full
 constexpr int kErrRange = 2;        // key outside the grid
 constexpr int kErrExchange = 4;     // peer-memory halo exchange: a peer's frame never arrived (bnv_p2p.cu)
+
+// floor (0) / ceil (1) flavour of corner k per axis, get_neighbors' order (src/models/fusion/utils.py:98-167):
+// k: (f,f,f) (c,f,f) (f,c,f) (f,f,c) (c,c,f) (c,f,c) (f,c,c) (c,c,c)
+__host__ __device__ constexpr int corner_sx(int k) { return (0xB2 >> k) & 1; }
+__host__ __device__ constexpr int corner_sy(int k) { return (0xD4 >> k) & 1; }
+__host__ __device__ constexpr int corner_sz(int k) { return (0xE8 >> k) & 1; }
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

@@ -66,21 +66,14 @@ __global__ void compact_pts_kernel(const float* __restrict__ pts, const int32_t*
 // ------------------------------------------------------------------------------------------- //
 constexpr int kPreThreads = kTileW * kTileH;   // 256: one 32 x 8 pixel tile (a warp = 32 pixels of one image row)
 
-// The (key, run length) pairs of a warp, lane j takes pairs j, j + 32, ...: NP = ceil(n_runs / 32) independent 32-bit
-// atomics per lane on the LOW word of the table entries (the count).  The first NP - 1 groups are full: unconditional,
-// straight-line code, so that all round trips to L2 are in flight before the first result is read; only the last,
-// partial group is predicated.  (Padding the partial groups with no-op atomics on a dummy word, as this kernel first
-// did, cost more than the real ones: 1.8 M atomic sectors per frame, two thirds of them padding -- profiles/r2e.)
-// Returns the mask of pairs whose voxel this lane touched first (count was 0).
+// NP (key, count) pairs per thread: independent 32-bit atomics on the LOW word of the table entries (the count).  The
+// first NP - 1 pairs exist for every lane of the warp: unconditional, straight-line code, so that all round trips to
+// L2 are in flight before the first result is read; only the last one is predicated.  (Padding with no-op atomics on
+// a dummy word, as this kernel first did, doubled the atomic traffic -- profiles/r2e.)
+// Returns the mask of pairs whose voxel this thread touched first (count was 0).
 template <int NP>
-__device__ __forceinline__ uint32_t claim_runs(const MapDev& m, int frame, const int2* __restrict__ runs, int n_runs, int lane,
-                                               int2 (&pr)[8]) {
+__device__ __forceinline__ uint32_t claim_pairs(const MapDev& m, int frame, const int2 (&pr)[8]) {
   unsigned int old[NP];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = j * 32 + lane;
-    pr[j] = (j < NP && i < n_runs) ? runs[i] : make_int2(-1, 0);
-  }
 #pragma unroll
   for (int j = 0; j < NP - 1; ++j)
     old[j] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[j].x, frame)), (unsigned int)pr[j].y);
@@ -92,12 +85,6 @@ __device__ __forceinline__ uint32_t claim_runs(const MapDev& m, int frame, const
   for (int j = 0; j < NP; ++j)
     if (old[j] == 0u) win |= 1u << j;
   return win;
-}
-
-__device__ __forceinline__ uint32_t claim_none(int2 (&pr)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) pr[j] = make_int2(-1, 0);
-  return 0;
 }
 
 // `frame` = position of the frame in its batch (0 for a single frame): selects the frame's word of every table entry
@@ -173,50 +160,78 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     fl[a] = floorf(c[a]);
     ce[a] = ceilf(c[a]);
   }
-  // ---- runs of lanes whose corner k is the same owned voxel -> (key, run length) pairs, compacted per warp ----
-  // Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE 64-bit atomicAdd of its length.
-  // The pairs are compacted into a per-warp shared-memory list first, so that the atomics are issued by dense,
-  // unconditional, independent instructions (lane j takes pairs j, j + 32, ...): all of a lane's round trips to L2
-  // are in flight together.  (Issued in place under `if (head)`, the compiler sinks each result test into its branch:
-  // eight serialised L2 round trips per thread, 55 % of this kernel's stall samples in profiles/r2a.)
-  uint32_t own = 0;
+  // ---- runs of lanes with the same 2 x 2 x 2 corner block -> (key, run length) pairs per owned corner, compacted per
+  // warp.  Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE atomicAdd of its length per
+  // corner.  Two pixels share the voxel of one corner exactly when they share all eight (same floor voxel, same
+  // ceil - floor pattern), so the runs are found once per pixel, not once per corner.  The pairs go to a per-warp
+  // shared-memory list first, so that the atomics are issued by dense, independent instructions (lane j takes pairs
+  // j, j + 32, ...): all of a lane's round trips to L2 are in flight together.  (Issued in place under `if (head)`, the
+  // compiler sinks each result test into its branch: eight serialised L2 round trips per thread, 55 % of this kernel's
+  // stall samples in profiles/r2a.)
   const bool sharded = g.world > 1;                                      // block-uniform
-  int n_runs = 0;                                                        // warp-uniform
+  const int fx = (int)fl[0], fy = (int)fl[1], fz = (int)fl[2];
+  const int ex = (int)ce[0] - fx, ey = (int)ce[1] - fy, ez = (int)ce[2] - fz;          // 0 or 1 each
+  const int32_t key0 = inb ? fx * g.nyz + fy * g.n[2] + fz : -1 - lane;  // rule A5 (int32); negatives never merge
+  const int32_t pat = ex | (ey << 1) | (ez << 2);
+  uint32_t own = inb ? 0xffu : 0u;
+  if (sharded && inb) {
+    own = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float nb[3];
-    corner_of(k, fl, ce, nb);                                            // rule A3 (modules.py:178-247)
-    const int ix = (int)nb[0], iy = (int)nb[1], iz = (int)nb[2];
-    bool o = inb;
-    if (sharded) o = o & (owner_of(g, ix, iy, iz) == g.rank);
-    const int32_t key = o ? ix * g.nyz + iy * g.n[2] + iz : -1 - lane;   // rule A5 (int32); negatives never merge
-    own |= (o ? 1u : 0u) << k;
-    const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || prev != key;
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t real = __ballot_sync(0xffffffffu, head && o);
-    if (head && o) {
-      const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
-      const int run = rest ? __ffs(rest) : 32 - lane;
-      s_runs[warp][n_runs + __popc(real & ((1u << lane) - 1u))] = make_int2(key, run);
+    for (int k = 0; k < 8; ++k)                                          // rule A3 corner order (modules.py:178-247)
+      own |= (owner_of(g, fx + (corner_sx(k) ? ex : 0), fy + (corner_sy(k) ? ey : 0), fz + (corner_sz(k) ? ez : 0)) == g.rank ? 1u : 0u) << k;
+  }
+  const int32_t prev_key = __shfl_up_sync(0xffffffffu, key0, 1), prev_pat = __shfl_up_sync(0xffffffffu, pat, 1);
+  const bool head = lane == 0 || prev_key != key0 || prev_pat != pat;
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const bool lead = head && own != 0;                                    // this lane writes its run's pairs
+  int n_runs, at;                                                        // pairs of the warp (uniform) / before this lane
+  if (!sharded) {
+    const uint32_t real = __ballot_sync(0xffffffffu, lead);
+    at = 8 * __popc(real & ((1u << lane) - 1u));
+    n_runs = 8 * __popc(real);
+  } else {
+    const int mine = lead ? __popc(own) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-    n_runs += __popc(real);
+    at = incl - mine;
+    n_runs = __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lead) {
+    const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
+    const int run = rest ? __ffs(rest) : 32 - lane;
+    const int dx = ex * g.nyz, dy = ey * g.n[2];
+    int2* out = s_runs[warp] + at;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if ((own >> k) & 1u)
+        *out++ = make_int2(key0 + (corner_sx(k) ? dx : 0) + (corner_sy(k) ? dy : 0) + (corner_sz(k) ? ez : 0), run);
   }
   __syncwarp();
-  // ---- claim + count: lane j takes pairs j, j + 32, ... ----
+  // ---- claim + count: lane j takes the warp's pairs j, j + 32, ... ----
+  // (Merging the tile's pairs per voxel in a shared-memory hash table first -- ~6 x fewer global atomics -- was tried
+  // in round 2: 148 instead of 153 us on 7 frames, 31 instead of 27 us on one; the claims cost a round trip per block,
+  // not a share of the atomic throughput.)
   int2 pr[8];
-  const int2* runs = s_runs[warp];
-  uint32_t win;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = j * 32 + lane;
+    pr[j] = i < n_runs ? s_runs[warp][i] : make_int2(-1, 0);
+  }
+  uint32_t win = 0;
   switch ((dbg & 1) ? 0 : (n_runs + 31) >> 5) {                        // warp-uniform
-    case 1: win = claim_runs<1>(m, frame, runs, n_runs, lane, pr); break;
-    case 2: win = claim_runs<2>(m, frame, runs, n_runs, lane, pr); break;
-    case 3: win = claim_runs<3>(m, frame, runs, n_runs, lane, pr); break;
-    case 4: win = claim_runs<4>(m, frame, runs, n_runs, lane, pr); break;
-    case 5: win = claim_runs<5>(m, frame, runs, n_runs, lane, pr); break;
-    case 6: win = claim_runs<6>(m, frame, runs, n_runs, lane, pr); break;
-    case 7: win = claim_runs<7>(m, frame, runs, n_runs, lane, pr); break;
-    case 8: win = claim_runs<8>(m, frame, runs, n_runs, lane, pr); break;
-    default: win = claim_none(pr); break;
+    case 1: win = claim_pairs<1>(m, frame, pr); break;
+    case 2: win = claim_pairs<2>(m, frame, pr); break;
+    case 3: win = claim_pairs<3>(m, frame, pr); break;
+    case 4: win = claim_pairs<4>(m, frame, pr); break;
+    case 5: win = claim_pairs<5>(m, frame, pr); break;
+    case 6: win = claim_pairs<6>(m, frame, pr); break;
+    case 7: win = claim_pairs<7>(m, frame, pr); break;
+    case 8: win = claim_pairs<8>(m, frame, pr); break;
+    default: break;
   }
   // ---- first touchers allocate dense scratch rows; in-bounds points get a record slot ---------------------
   const int n_new = __popc(win);
@@ -356,14 +371,14 @@ __global__ void __launch_bounds__(256) finalize_fused_kernel(MapDev m, int min_p
   finalize_publish(m, integrated, n_touched, stats, user_stats, user_navg);
 }
 
-// the same for a batch of frames: the first of a voxel's (frame, voxel) scratch rows to arrive makes its 8-lane group
-// do all the voxel's frames
-template <int S, bool F32>
-__global__ void __launch_bounds__(256, S == 8 ? 4 : 2) finalize_batch_kernel(MapDev m, int min_pts, unsigned int seq, long long* __restrict__ stats,
-                                                             long long* __restrict__ user_stats, float* __restrict__ user_navg) {
+// the same for a batch of frames: the first of a voxel's (frame, voxel) scratch rows to arrive makes its thread do all
+// the voxel's frames
+template <bool F32>
+__global__ void __launch_bounds__(256, 2) finalize_batch_kernel(MapDev m, int min_pts, unsigned int seq, long long* __restrict__ stats,
+                                                                long long* __restrict__ user_stats, float* __restrict__ user_navg) {
   grid_dependency_wait();                               // the encoder MLP kernel
   const int n_touched = m.ctr[1];
-  const int integrated = finalize_batch_rows<S, F32>(m, min_pts, seq, n_touched);
+  const int integrated = finalize_batch_rows<F32>(m, min_pts, seq, n_touched);
   finalize_publish(m, integrated, n_touched, stats, user_stats, user_navg);
 }
 
@@ -715,10 +730,8 @@ int bnv_fuse_frames(bnv_map_t* map, const uint16_t* const* depth, int n_frames, 
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
   if (++map->batch_seq == 0u) map->batch_seq = 1u;     // 0 is the cleared lock word (a wrap after 2^32 batches)
   {
-    const dim3 grid(148 * 4), block(256);
-    const bool f32 = mode == BNV_MLP_TC16, wide = map->d.fshift == 4;
-    auto kernel = wide ? (f32 ? finalize_batch_kernel<16, true> : finalize_batch_kernel<16, false>)
-                       : (f32 ? finalize_batch_kernel<8, true> : finalize_batch_kernel<8, false>);
+    const dim3 grid(148 * 2), block(256);
+    auto kernel = mode == BNV_MLP_TC16 ? finalize_batch_kernel<true> : finalize_batch_kernel<false>;
     BNV_CUDA(launch_pdl(kernel, grid, block, 0, s, map->d, min_pts, map->batch_seq, (long long*)map->stats,
                         (long long*)batch_stats, navg));
   }

@@ -100,95 +100,105 @@ __device__ __forceinline__ int finalize_rows(const MapDev& m, int min_pts, bool 
   return integrated;
 }
 
-// Frame batch (bnv_fuse_frames): scratch rows are (frame, voxel) pairs; ONE group of 8 lanes per voxel (a lane per
-// feature) applies the voxel's frames in frame order, which is exactly the sequence of _update calls the per-frame path
-// makes, with the voxel's weight and features held in registers in between (one read-modify-write of the map per voxel
-// and batch instead of one per frame).  The voxel's rows are all requested before the first one is used -- the frame
-// loop is then pure arithmetic -- and the stored voxel is read alongside them: three dependent memory round trips per
-// voxel whatever the batch size.  (One thread per voxel walking its rows one after the other ran 213 us on 7 frames,
-// 99 % of it waiting for the row of the next frame: profiles/r2e.)
-// The group is chosen by the first of the voxel's rows to swap the batch sequence number into the cell's lock word
-// (the last of its S table words); the lock is never released -- the next batch brings a new number -- so a row that
-// arrives late can never see a half-cleared cell.  S = table words per cell (frames <= S - 1).
-//
-// finalize_batch_voxel: all frames of one voxel; `sub` = feature of this lane, `gmask` = the group's lanes (converged).
-// Returns the number of (frame, voxel) pairs integrated (on the group's first lane, 0 on the others).
-template <int S, bool F32>
-__device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts, int32_t key, int sub, unsigned gmask) {
+// Frame batch (bnv_fuse_frames): scratch rows are (frame, voxel) pairs; ONE thread per voxel applies the voxel's frames
+// in frame order, which is exactly the sequence of _update calls the per-frame path makes, with the voxel's weight and
+// features held in registers in between (one read-modify-write of the map per voxel and batch instead of one per
+// frame).  The voxel's rows are ALL requested before the first one is used (unconditional 16-byte loads, an untouched
+// frame reads row 0 and ignores it) and the stored voxel is read alongside them: three dependent memory round trips
+// per voxel whatever the batch size; the frame loop is then pure arithmetic.  (Walking the rows one after the other
+// ran 213 us on 7 frames, 99 % of it waiting for the next frame's row; 8 lanes per voxel kept an eighth as many voxels
+// in flight and ran 86 us -- profiles/r2e.)
+// The thread is chosen by the first of the voxel's rows to swap the batch sequence number into the cell's lock word
+// (the last of its kCellWords table words); the lock is never released -- the next batch brings a new number -- so a
+// row that arrives late can never see a half-cleared cell.
+constexpr int kCellWords = 8;                                     // 2^fshift: kMaxBatch frame words + the lock word
+static_assert(kMaxBatch == kCellWords - 1, "one table word per frame of a batch plus the lock");
+
+// all frames of one voxel; returns the number of (frame, voxel) pairs integrated
+template <bool F32>
+__device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts, int32_t key) {
+  constexpr int S = kCellWords;
   unsigned long long* ent = ft_entry(m, key, 0);
   int32_t slot = m.table[key];
   unsigned long long e[S];
 #pragma unroll
-  for (int j = 0; j < S / 2; ++j) {                               // the cell's words: S / 2 16-byte loads, L1 bypassed
+  for (int j = 0; j < S / 2; ++j) {                               // the cell's words: four 16-byte loads, L1 bypassed
     const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(ent) + j);
     e[2 * j] = v.x;
     e[2 * j + 1] = v.y;
   }
-  // this lane's feature of every frame's scratch row: independent loads, all in flight
-  float rawf[S - 1];
-  long long rawi[F32 ? 1 : S - 1];
+  float4 ra[F32 ? S - 1 : 1], rb[F32 ? S - 1 : 1];                 // tensor-core mode: the fp32 sums of every frame
+  if (F32) {
 #pragma unroll
-  for (int fr = 0; fr < S - 1; ++fr) {
-    rawf[fr] = 0.f;
-    if (!F32) rawi[F32 ? 0 : fr] = 0;
-    if (ft_count(e[fr]) != 0) {
-      const size_t at = (size_t)ft_row(e[fr]) * kFeat + sub;
-      if (F32) rawf[fr] = __ldcg(reinterpret_cast<const float*>(m.fsum) + at);
-      else rawi[F32 ? 0 : fr] = __ldcg(m.fsum + at);
+    for (int fr = 0; fr < S - 1; ++fr) {
+      const int32_t row = ft_count(e[fr]) != 0 ? ft_row(e[fr]) : 0;
+      const float4* s4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(m.fsum) + (size_t)row * kFeat);
+      ra[F32 ? fr : 0] = __ldcg(s4);
+      rb[F32 ? fr : 0] = __ldcg(s4 + 1);
     }
   }
   // the stored voxel (if any): independent of the rows
-  float w = 0.f, f = 0.f;
-  if (slot >= 0) {
-    w = m.weights[slot];
-    f = m.feats[(size_t)slot * kFeat + sub];
-  }
-  // re-arm the scratch rows and the cell's frame words
+  float w = 0.f;
+  float f[kFeat];
 #pragma unroll
-  for (int fr = 0; fr < S - 1; ++fr)
-    if (ft_count(e[fr]) != 0) {
-      const size_t at = (size_t)ft_row(e[fr]) * kFeat + sub;
-      if (F32) reinterpret_cast<float*>(m.fsum)[at] = 0.f;
-      else m.fsum[at] = 0;
-      if (sub == 0) ent[fr] = 0ull;
-    }
+  for (int j = 0; j < kFeat; ++j) f[j] = 0.f;
+  if (slot >= 0) {
+    const float4* f4 = reinterpret_cast<const float4*>(m.feats + (size_t)slot * kFeat);
+    const float4 oa = f4[0], ob = f4[1];
+    w = m.weights[slot];
+    f[0] = oa.x; f[1] = oa.y; f[2] = oa.z; f[3] = oa.w;
+    f[4] = ob.x; f[5] = ob.y; f[6] = ob.z; f[7] = ob.w;
+  }
   int integrated = 0;
   bool dead = false;
 #pragma unroll
   for (int fr = 0; fr < S - 1; ++fr) {
     const int32_t cnt = ft_count(e[fr]);
-    if (cnt < min_pts || cnt == 0 || dead) continue;              // local_point_fusion.py:143-147
-    // scatter_mean, local_point_fusion.py:125 (same roundings as finalize_rows)
-    const float mean = F32 ? __fdiv_rn(rawf[fr], (float)cnt) : (float)(((double)rawi[F32 ? 0 : fr] / kFixScale) / (double)cnt);
-    if (slot < 0) {                                               // first frame that integrates a new voxel
-      int32_t s2 = -1;
-      if (sub == 0) {
-        s2 = atomicAdd(&m.ctr[0], 1);
-        if (s2 >= m.cap) {
-          atomicOr(&m.ctr[2], kErrCapacity);
-          s2 = -1;
-        } else {
-          m.table[key] = s2;
-          m.keys[s2] = key;
-          m.hits[s2] = 0.f;
-        }
+    if (cnt == 0) continue;                                       // frame fr did not touch the voxel
+    const int32_t row = ft_row(e[fr]);
+    ent[fr] = 0ull;                                               // re-arm the cell's frame word and the scratch row
+    float mean[kFeat];                                            // scatter_mean, local_point_fusion.py:125
+    if (F32) {
+      float4* s4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.fsum) + (size_t)row * kFeat);
+      s4[0] = s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 a = ra[F32 ? fr : 0], b = rb[F32 ? fr : 0];
+      const float sv[kFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float fc = (float)cnt;
+#pragma unroll
+      for (int j = 0; j < kFeat; ++j) mean[j] = __fdiv_rn(sv[j], fc);
+    } else {
+      longlong2* s2 = reinterpret_cast<longlong2*>(m.fsum + (size_t)row * kFeat);
+#pragma unroll
+      for (int j = 0; j < kFeat / 2; ++j) {
+        const longlong2 v = s2[j];
+        s2[j] = make_longlong2(0, 0);
+        mean[2 * j] = (float)(((double)v.x / kFixScale) / (double)cnt);
+        mean[2 * j + 1] = (float)(((double)v.y / kFixScale) / (double)cnt);
       }
-      s2 = __shfl_sync(gmask, s2, __ffs(gmask) - 1);
-      if (s2 < 0) {
+    }
+    if (cnt < min_pts || dead) continue;                          // local_point_fusion.py:143-147
+    if (slot < 0) {                                               // first frame that integrates a new voxel
+      slot = atomicAdd(&m.ctr[0], 1);
+      if (slot >= m.cap) {
+        atomicOr(&m.ctr[2], kErrCapacity);
         dead = true;
         continue;
       }
-      slot = s2;
+      m.table[key] = slot;
+      m.keys[slot] = key;
+      m.hits[slot] = 0.f;
     }
     const float w_new = fminf(__fmul_rn((float)cnt, 0.03125f), 1.0f);   // clip(count/32, max=1)
     const float w_sum = __fadd_rn(w, w_new);
-    f = fuse_feat(f, w, mean, w_new, w_sum);
+#pragma unroll
+    for (int j = 0; j < kFeat; ++j) f[j] = fuse_feat(f[j], w, mean[j], w_new, w_sum);
     w = w_sum;
     ++integrated;
   }
   if (integrated == 0) return 0;
-  m.feats[(size_t)slot * kFeat + sub] = f;
-  if (sub != 0) return 0;
+  float4* f4 = reinterpret_cast<float4*>(m.feats + (size_t)slot * kFeat);
+  f4[0] = make_float4(f[0], f[1], f[2], f[3]);
+  f4[1] = make_float4(f[4], f[5], f[6], f[7]);
   m.weights[slot] = w;
   if (m.dirty_list) {                                             // tile shard: another rank may need it as a corner
     const int kx = key / m.g.nyz, kr = key - kx * m.g.nyz, ky = kr / m.g.n[2], kz = kr - ky * m.g.n[2];
@@ -201,29 +211,26 @@ __device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts
   return integrated;
 }
 
-// A block takes chunks of kBatchRows scratch rows (handed out by an atomic counter, ctr[6]: the chunks' costs differ
-// with their share of winners): (1) every thread swaps the sequence number into the lock words of kBatchRows / blockDim
-// rows (independent atomics, all in flight) and the winners' voxels go to a shared-memory list; (2) the list is spread
-// densely over the block's 8-lane groups.  Most rows lose (a voxel is touched by most frames of the batch), so the
-// per-voxel work runs in full warps.
-constexpr int kBatchRows = 512;
-template <int S, bool F32>
+// A block takes chunks of kBatchRows scratch rows, handed out by an atomic counter (ctr[6]; the next chunk's number is
+// fetched while the current one is processed): (1) every thread swaps the sequence number into the lock words of
+// kBatchRows / blockDim rows (independent atomics, all in flight) and the winners' voxels go to a shared-memory list;
+// (2) the list is spread densely over the block's threads.  Most rows lose (a voxel is touched by most frames of the
+// batch), so the per-voxel work runs in full warps.
+constexpr int kBatchRows = 1024;
+template <bool F32>
 __device__ __forceinline__ int finalize_batch_rows(const MapDev& m, int min_pts, unsigned int seq, int n_touched) {
   __shared__ int32_t s_lead[kBatchRows];
-  __shared__ int s_n, s_chunk;
+  __shared__ int s_n[2], s_chunk[2];                              // double-buffered: two barriers per chunk suffice
   constexpr int R = kBatchRows / 256;
-  const int sub = threadIdx.x & 7;
-  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   const int n_chunks = (n_touched + kBatchRows - 1) / kBatchRows;
   int integrated = 0;
-  for (;;) {
-    if (threadIdx.x == 0) {
-      s_n = 0;
-      s_chunk = atomicAdd(&m.ctr[6], 1);
-    }
+  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(&m.ctr[6], 1);
+  for (int it = 0;; ++it) {
+    if (threadIdx.x == 0) s_n[it & 1] = 0;
     __syncthreads();
-    const int chunk = s_chunk;
+    const int chunk = s_chunk[it & 1];
     if (chunk >= n_chunks) break;                                 // block-uniform
+    if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = atomicAdd(&m.ctr[6], 1);
     const int64_t base = (int64_t)chunk * kBatchRows;
     int32_t key[R];
     unsigned int old[R];
@@ -235,18 +242,17 @@ __device__ __forceinline__ int finalize_batch_rows(const MapDev& m, int min_pts,
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       old[r] = seq;
-      if (key[r] >= 0) old[r] = atomicExch(reinterpret_cast<unsigned int*>(ft_entry(m, key[r], S - 1)), seq);
+      if (key[r] >= 0) old[r] = atomicExch(reinterpret_cast<unsigned int*>(ft_entry(m, key[r], kCellWords - 1)), seq);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
       if (old[r] != seq) {
-        s_lead[atomicAdd(&s_n, 1)] = key[r];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + key[r]));      // the winner's group reads it next
+        s_lead[atomicAdd(&s_n[it & 1], 1)] = key[r];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + key[r]));      // the winner's thread reads it next
       }
     __syncthreads();
-    const int n_lead = s_n;
-    for (int i = threadIdx.x >> 3; i < n_lead; i += 32) integrated += finalize_batch_voxel<S, F32>(m, min_pts, s_lead[i], sub, gmask);
-    __syncthreads();
+    const int n_lead = s_n[it & 1];
+    for (int i = threadIdx.x; i < n_lead; i += 256) integrated += finalize_batch_voxel<F32>(m, min_pts, s_lead[i]);
   }
   return integrated;
 }

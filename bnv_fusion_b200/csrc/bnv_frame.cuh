@@ -12,11 +12,20 @@ struct Camera {
   int H, W;
 };
 
+// uint16 millimetres / 1000. in float64, correctly rounded, without the division routine: with r = RN(1/1000) and
+// q0 = RN(d r), the residual d - 1000 q0 is exact in one fma and RN(q0 + residual r) is the correctly rounded
+// quotient (Markstein); checked against d / 1000.0 for every uint16 d by tests/test_div1000.py.
+__device__ __forceinline__ double mm_to_m(uint16_t d) {
+  const double a = (double)d;
+  const double q0 = __dmul_rn(a, 0.001);
+  return __fma_rn(__fma_rn(-q0, 1000.0, a), 0.001, q0);
+}
+
 // masked metric depth of a pixel with replicate padding (load_depth, src/utils/common.py:93-112)
 __device__ __forceinline__ double depth_at(const uint16_t* __restrict__ d, const Camera& cam, int u, int v) {
   u = min(max(u, 0), cam.W - 1);
   v = min(max(v, 0), cam.H - 1);
-  const double z = (double)__ldg(d + (size_t)v * cam.W + u) / 1000.0;
+  const double z = mm_to_m(__ldg(d + (size_t)v * cam.W + u));
   return (z > 0.0 && z < cam.max_depth) ? z : 0.0;
 }
 
@@ -28,22 +37,24 @@ __device__ __forceinline__ void backproject_finish(const double (&X)[3][3], cons
                                                    const double (&Z)[3][3], double zc, int u, int v, const Camera& cam,
                                                    float (&out)[6]) {
   const double e = 0.125;
+  // The six products of a Sobel sum are exact (powers of two times a double far from the subnormal range), so
+  // fma(e, P, a) rounds exactly like the reference's separate multiply and add: same bits, half the instructions.
   auto sobx = [&](const double (&P)[3][3]) {
     double a = __dmul_rn(-e, P[0][0]);
-    a = __dadd_rn(a, __dmul_rn(e, P[0][2]));
-    a = __dadd_rn(a, __dmul_rn(-2 * e, P[1][0]));
-    a = __dadd_rn(a, __dmul_rn(2 * e, P[1][2]));
-    a = __dadd_rn(a, __dmul_rn(-e, P[2][0]));
-    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    a = __fma_rn(e, P[0][2], a);
+    a = __fma_rn(-2 * e, P[1][0], a);
+    a = __fma_rn(2 * e, P[1][2], a);
+    a = __fma_rn(-e, P[2][0], a);
+    a = __fma_rn(e, P[2][2], a);
     return a;
   };
   auto soby = [&](const double (&P)[3][3]) {
     double a = __dmul_rn(-e, P[0][0]);
-    a = __dadd_rn(a, __dmul_rn(-2 * e, P[0][1]));
-    a = __dadd_rn(a, __dmul_rn(-e, P[0][2]));
-    a = __dadd_rn(a, __dmul_rn(e, P[2][0]));
-    a = __dadd_rn(a, __dmul_rn(2 * e, P[2][1]));
-    a = __dadd_rn(a, __dmul_rn(e, P[2][2]));
+    a = __fma_rn(-2 * e, P[0][1], a);
+    a = __fma_rn(-e, P[0][2], a);
+    a = __fma_rn(e, P[2][0], a);
+    a = __fma_rn(2 * e, P[2][1], a);
+    a = __fma_rn(e, P[2][2], a);
     return a;
   };
   const double gx0 = sobx(X), gx1 = sobx(Y), gx2 = sobx(Z);
@@ -107,9 +118,8 @@ __device__ __forceinline__ void stage_frame_tile(FrameTile& t, const uint16_t* _
   for (int i = threadIdx.x; i < (kTileH + 2) * (kTileW + 2); i += blockDim.x) {
     const int yy = i / (kTileW + 2), xx = i - yy * (kTileW + 2);
     const int uu = min(max(u0 - 1 + xx, 0), cam.W - 1), vv = min(max(v0 - 1 + yy, 0), cam.H - 1);
-    // load_depth (src/utils/common.py:93): uint16 millimetres / 1000. in float64 -- one correctly rounded division
-    // per staged pixel (a lookup table would cost a second dependent memory round trip per tile)
-    const double z = __ddiv_rn((double)__ldg(depth + (size_t)vv * cam.W + uu), 1000.0);
+    // load_depth (src/utils/common.py:93): uint16 millimetres / 1000. in float64
+    const double z = mm_to_m(__ldg(depth + (size_t)vv * cam.W + uu));
     t.z[yy][xx] = (z > 0.0 && z < cam.max_depth) ? z : 0.0;
   }
   if (threadIdx.x < kTileW + 2) {

@@ -382,7 +382,7 @@ int bnv_map_set_frame_batch(bnv_map_t* m, int n_frames) {
   BNV_CUDA(cudaSetDevice(m->device));
   BNV_CUDA(cudaDeviceSynchronize());             // no frame may be in flight while the per-frame table is replaced
   MapDev& d = m->d;
-  const int shift = n_frames == 0 ? 0 : n_frames < 8 ? 3 : 4;
+  const int shift = n_frames == 0 ? 0 : 3;       // 8 table words per grid cell: kMaxBatch frames + the finalize lock
   const int64_t pairs = d.g.n_vox * (n_frames > 1 ? n_frames : 1);       // (frame, voxel) pairs a call can touch
   const int64_t fcap = m->max_points * 8 < pairs ? m->max_points * 8 : pairs;
   if (shift != d.fshift) {

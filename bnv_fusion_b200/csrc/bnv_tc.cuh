@@ -242,11 +242,6 @@ __device__ __forceinline__ void wg_sync(int bar_id) { asm volatile("bar.sync %0,
 constexpr int kInCol = 96;
 constexpr int kOutCol = 112;
 
-// floor (0) / ceil (1) flavour of corner k per axis, get_neighbors' order (src/models/fusion/utils.py:98-167):
-// k: (f,f,f) (c,f,f) (f,c,f) (f,f,c) (c,c,f) (c,f,c) (f,c,c) (c,c,c)
-__host__ __device__ constexpr int corner_sx(int k) { return (0xB2 >> k) & 1; }
-__host__ __device__ constexpr int corner_sy(int k) { return (0xD4 >> k) & 1; }
-__host__ __device__ constexpr int corner_sz(int k) { return (0xE8 >> k) & 1; }
 
 // one lane of a converged warp (elect.sync): with a warp-uniform enclosing branch and warp-uniform
 // operands ptxas emits straight-line UTCHMMA / UTCBAR; a thread-divergent `if (tid == x)` instead makes it

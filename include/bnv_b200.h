@@ -203,9 +203,9 @@ int bnv_fuse_frame_host(bnv_map_t* map, const uint16_t* depth_mm_host, int H, in
  * which amortises the kernels' fixed latencies over the batch (offline scenes, or a live stream that tolerates
  * n_frames of delay).
  *
- * bnv_map_set_frame_batch lays the per-frame table out for batches of up to n_frames (<= 15) frames: 8 (n_frames < 8)
- * or 16 table words per grid cell instead of 1; n_frames == 0 restores the single-frame layout.  The map must have
- * been created with max_points >= n_frames * H * W.  Synchronises the device. */
+ * bnv_map_set_frame_batch lays the per-frame table out for batches of up to n_frames (<= 7) frames: 8 table words
+ * per grid cell instead of 1 (8.6 GB instead of 1.1 GB for a 512^3 grid); n_frames == 0 restores the single-frame
+ * layout.  The map must have been created with max_points >= n_frames * H * W.  Synchronises the device. */
 int bnv_map_set_frame_batch(bnv_map_t* map, int n_frames);
 /* depth_mm_dev: HOST array of n_frames device pointers ([H,W] uint16 each); K_host [n_frames,3,3], T_wc_host
  * [n_frames,4,4] row-major fp32.  batch_stats_dev (nullable) int64[4] = the four bnv_fuse_frame statistics summed

@@ -39,9 +39,9 @@ def _assert_maps_equal(a, b, exact):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tc16"])
-@pytest.mark.parametrize("n", [1, 3, 7, 8, 15])
+@pytest.mark.parametrize("n", [1, 2, 4, 7])
 def test_batch_equals_sequential(model, dev, mode, n):
-    """n = 1..7 use 8 table words per grid cell, 8..15 use 16; statistics are the sums of the per-frame statistics."""
+    """up to 7 frames per call (8 table words per grid cell); statistics are the sums of the per-frame statistics."""
     from bnv_fusion_b200 import config
     config.set_mlp_mode(mode)
     spec = synth.stream_spec("parity64")
@@ -108,23 +108,23 @@ def test_batch_vs_oracle(model, tcnn_params, dev):
 
 
 def test_batch_lounge_full_frames_tc(model, dev):
-    """headline shape: two batches of 8 full 640x480 frames into the 512^3 grid on the tensor cores vs 16 single-frame
-    calls: ids / weights exact, features within fp32 summation-order noise"""
+    """headline shape: batches of 7, 7 and 2 full 640x480 frames into the 512^3 grid on the tensor cores vs 16
+    single-frame calls: ids / weights exact, features within fp32 summation-order noise"""
     from bnv_fusion_b200 import config
     config.set_mlp_mode("tc16")
     spec = synth.stream_spec("lounge")
     fr, Ks, Ts = _frames(spec, 16, seed=0)
     devf = [_depth_to_dev(d, dev) for d, _, _ in fr]
     va = _volume(spec, dev, pool_capacity=1 << 20)
-    vb = _volume(spec, dev, pool_capacity=1 << 20, frame_batch=8)
+    vb = _volume(spec, dev, pool_capacity=1 << 20, frame_batch=7)
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     total = np.zeros(4, np.int64)
     for i in range(16):
         model.fuse_depth_frame(va, devf[i], fr[i][1], fr[i][2], spec.max_depth, stats=stats)
         total += np.asarray(stats.tolist())
     got = np.zeros(4, np.int64)
-    for b in range(2):
-        model.fuse_depth_frames(vb, devf[8 * b:8 * b + 8], Ks[8 * b:8 * b + 8], Ts[8 * b:8 * b + 8], spec.max_depth, stats=stats)
+    for sl in (slice(0, 7), slice(7, 14), slice(14, 16)):
+        model.fuse_depth_frames(vb, devf[sl], Ks[sl], Ts[sl], spec.max_depth, stats=stats)
         got += np.asarray(stats.tolist())
     assert got.tolist() == total.tolist()
     va.check_status(); vb.check_status()
@@ -161,7 +161,7 @@ def test_batch_host_call_and_errors(model, dev):
     with pytest.raises(RuntimeError):                       # a volume without the batch layout
         model.fuse_depth_frames(plain, devf[0:2], Ks[0:2], Ts[0:2], spec.max_depth)
     with pytest.raises(RuntimeError):
-        plain.set_frame_batch(16)
+        plain.set_frame_batch(8)                            # at most 7 frames per call
     small = _volume(spec, dev, pool_capacity=1 << 16, max_points=64 * 64)
     small.set_frame_batch(2)
     with pytest.raises(RuntimeError):                       # max_points covers one frame only

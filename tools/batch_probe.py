@@ -17,7 +17,11 @@ from bnv_fusion_b200.volume import SparseVolume  # noqa: E402
 
 
 def main():
-    sizes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 7, 8, 15]
+    sizes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 4, 7]
+    dbg = int(os.environ.get("BNV_PROBE_DBG", "0"))   # prepass ablation flags (timing only: the maps are garbage)
+    if dbg:
+        _lib.load().bnv_debug_prepass.argtypes = [C.c_int]
+        _lib.load().bnv_debug_prepass(dbg)
     dev = "cuda:0"
     lib = _lib.load()
     spec, frames = bench.make_frames(32)
@@ -74,12 +78,13 @@ def main():
         t1.record()
         torch.cuda.synchronize()
         warm = t0.elapsed_time(t1) / steps
-        vol.check_status()
+        if not dbg:
+            vol.check_status()
         nb = max(B, 1)
         st = np.mean(st, axis=0)
-        rec = {"batch": B, "ms_per_call": round(ms, 4), "frames_per_s_cold": round(nb * 1e3 / ms), "frames_per_s_warm": round(nb * 1e3 / warm),
+        rec = {"dbg": dbg, "batch": B, "ms_per_call": round(ms, 4), "frames_per_s_cold": round(nb * 1e3 / ms), "frames_per_s_warm": round(nb * 1e3 / warm),
                "prepass_ms": round(float(st[0]), 4), "encode_ms": round(float(st[1]), 4), "finalize_ms": round(float(st[2]), 4),
-               "voxels": int(vol.to_tensor()[0].shape[0])}
+               "voxels": 0 if dbg else int(vol.to_tensor()[0].shape[0])}
         print(json.dumps(rec), flush=True)
         out.append(rec)
         del vol
