@@ -85,7 +85,7 @@ struct MapDev {
   float* prec;          // [max_points, 8] compacted in-bounds point records of the frame: voxel-space xyz, normal, pad
   int32_t fcap;         // min(8 * max_points, n_vox * max(1, frames per batch))
   // device counters: [0] n_slots, [1] n_touched, [2] status bits, [3] finalize block counter, [4] n point records,
-  // [5] n dirty shell voxels, [6] chunk counter of the batch finalize
+  // [5] n dirty shell voxels
   int32_t* ctr;
   // tile shard (nullable): voxels on the shell of their brick that were integrated since the last boundary exchange
   // are remembered once each (flag per pool slot + list of slots, counter ctr[5]); bnv_map_halo_pack turns the list

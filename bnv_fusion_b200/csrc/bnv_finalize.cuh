@@ -23,6 +23,15 @@ __device__ __forceinline__ float fuse_feat(float f_old, float w_old, float f_new
   return __fdiv_rn(__fadd_rn(__fmul_rn(f_old, w_old), __fmul_rn(f_new, w_new)), w);
 }
 
+// Tensor-core mode: the features already carry the fp16 operand rounding of the MLP (1e-3), so the two divisions per
+// feature and frame -- mean = sum / count and the weighted average / (w_old + w_new) -- are done as one correctly
+// rounded reciprocal per voxel and frame and a multiplication per feature (<= 1 ulp of fp32 from the true quotient);
+// IEEE divisions were three quarters of the batch finalize's instructions.  The exact-parity mode keeps the reference's
+// true divisions.  Both finalize flavours use the same arithmetic, so a batch equals its frames one by one.
+__device__ __forceinline__ float fuse_feat_rcp(float f_old, float w_old, float f_new, float w_new, float rcp_w) {
+  return __fmul_rn(__fadd_rn(__fmul_rn(f_old, w_old), __fmul_rn(f_new, w_new)), rcp_w);
+}
+
 // One thread per touched voxel (dense scratch rows first, first + stride, ...): the work is a chain of dependent
 // scattered reads (key -> table entries -> map slot -> old features), i.e. latency x concurrency bound, so every
 // thread keeps its own voxel's chain in flight; the 32-byte scratch and feature rows move as two 16-byte accesses.
@@ -42,11 +51,11 @@ __device__ __forceinline__ int finalize_rows(const MapDev& m, int min_pts, bool 
       const float4 a = s4[0], b = s4[1];
       s4[0] = s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float s[kFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      // float32 sums / exact integer count: one correctly rounded float32 division (the float64 form of the exact-
-      // parity mode costs ~45 instructions per feature and was 90 % of this kernel's instruction count)
-      const float fc = (float)cnt;
+      // float32 sums x 1 / count (the float64 form of the exact-parity mode costs ~45 instructions per feature and
+      // was 90 % of this kernel's instruction count)
+      const float rc = __frcp_rn((float)cnt);
 #pragma unroll
-      for (int j = 0; j < kFeat; ++j) mean[j] = __fdiv_rn(s[j], fc);
+      for (int j = 0; j < kFeat; ++j) mean[j] = __fmul_rn(s[j], rc);
     } else {
       longlong2* s2 = reinterpret_cast<longlong2*>(m.fsum + (size_t)t * kFeat);
 #pragma unroll
@@ -82,8 +91,14 @@ __device__ __forceinline__ int finalize_rows(const MapDev& m, int min_pts, bool 
     const float w = __fadd_rn(w_old, w_new);
     const float f_old[kFeat] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
     float f_new[kFeat];
+    if (f32acc) {
+      const float rw = __frcp_rn(w);
 #pragma unroll
-    for (int j = 0; j < kFeat; ++j) f_new[j] = fuse_feat(f_old[j], w_old, mean[j], w_new, w);
+      for (int j = 0; j < kFeat; ++j) f_new[j] = fuse_feat_rcp(f_old[j], w_old, mean[j], w_new, rw);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFeat; ++j) f_new[j] = fuse_feat(f_old[j], w_old, mean[j], w_new, w);
+    }
     f4[0] = make_float4(f_new[0], f_new[1], f_new[2], f_new[3]);
     f4[1] = make_float4(f_new[4], f_new[5], f_new[6], f_new[7]);
     m.weights[slot] = w;
@@ -116,10 +131,9 @@ static_assert(kMaxBatch == kCellWords - 1, "one table word per frame of a batch 
 
 // all frames of one voxel; returns the number of (frame, voxel) pairs integrated
 template <bool F32>
-__device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts, int32_t key) {
+__device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts, int32_t key, int32_t slot) {
   constexpr int S = kCellWords;
   unsigned long long* ent = ft_entry(m, key, 0);
-  int32_t slot = m.table[key];
   unsigned long long e[S];
 #pragma unroll
   for (int j = 0; j < S / 2; ++j) {                               // the cell's words: four 16-byte loads, L1 bypassed
@@ -163,9 +177,9 @@ __device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts
       s4[0] = s4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 a = ra[F32 ? fr : 0], b = rb[F32 ? fr : 0];
       const float sv[kFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      const float fc = (float)cnt;
+      const float rc = __frcp_rn((float)cnt);
 #pragma unroll
-      for (int j = 0; j < kFeat; ++j) mean[j] = __fdiv_rn(sv[j], fc);
+      for (int j = 0; j < kFeat; ++j) mean[j] = __fmul_rn(sv[j], rc);
     } else {
       longlong2* s2 = reinterpret_cast<longlong2*>(m.fsum + (size_t)row * kFeat);
 #pragma unroll
@@ -190,8 +204,14 @@ __device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts
     }
     const float w_new = fminf(__fmul_rn((float)cnt, 0.03125f), 1.0f);   // clip(count/32, max=1)
     const float w_sum = __fadd_rn(w, w_new);
+    if (F32) {
+      const float rw = __frcp_rn(w_sum);
 #pragma unroll
-    for (int j = 0; j < kFeat; ++j) f[j] = fuse_feat(f[j], w, mean[j], w_new, w_sum);
+      for (int j = 0; j < kFeat; ++j) f[j] = fuse_feat_rcp(f[j], w, mean[j], w_new, rw);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFeat; ++j) f[j] = fuse_feat(f[j], w, mean[j], w_new, w_sum);
+    }
     w = w_sum;
     ++integrated;
   }
@@ -211,48 +231,54 @@ __device__ __forceinline__ int finalize_batch_voxel(const MapDev& m, int min_pts
   return integrated;
 }
 
-// A block takes chunks of kBatchRows scratch rows, handed out by an atomic counter (ctr[6]; the next chunk's number is
-// fetched while the current one is processed): (1) every thread swaps the sequence number into the lock words of
-// kBatchRows / blockDim rows (independent atomics, all in flight) and the winners' voxels go to a shared-memory list;
-// (2) the list is spread densely over the block's threads.  Most rows lose (a voxel is touched by most frames of the
-// batch), so the per-voxel work runs in full warps.
-constexpr int kBatchRows = 1024;
+// The scratch rows are split evenly over the blocks (up to kBatchRowsMax per block and sweep).  (1) Every thread swaps
+// the sequence number into the lock words of its rows -- independent atomics, four in flight per thread -- and the
+// winners look their voxel up in the persistent table right away (the stored voxel's lines are on their way into L2
+// while the other rows are still being resolved); the winners' (voxel, slot) pairs go to a shared-memory list.
+// (2) The list is spread densely over the block's threads.  Most rows lose (a voxel is touched by most frames of the
+// batch), so the heavy per-voxel work runs in full warps, and its memory round trips start from L2.
+constexpr int kBatchRowsMax = 4096;
 template <bool F32>
 __device__ __forceinline__ int finalize_batch_rows(const MapDev& m, int min_pts, unsigned int seq, int n_touched) {
-  __shared__ int32_t s_lead[kBatchRows];
-  __shared__ int s_n[2], s_chunk[2];                              // double-buffered: two barriers per chunk suffice
-  constexpr int R = kBatchRows / 256;
-  const int n_chunks = (n_touched + kBatchRows - 1) / kBatchRows;
+  __shared__ int32_t s_lead[kBatchRowsMax], s_slot[kBatchRowsMax];
+  __shared__ int s_n;
+  int per_block = (int)(((int64_t)n_touched + gridDim.x - 1) / gridDim.x);
+  per_block = min(kBatchRowsMax, (per_block + 255) & ~255);
   int integrated = 0;
-  if (threadIdx.x == 0) s_chunk[0] = atomicAdd(&m.ctr[6], 1);
-  for (int it = 0;; ++it) {
-    if (threadIdx.x == 0) s_n[it & 1] = 0;
+  for (int64_t base = (int64_t)blockIdx.x * per_block; base < n_touched; base += (int64_t)gridDim.x * per_block) {
+    __syncthreads();                                              // the previous sweep's list has been consumed
+    if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    const int chunk = s_chunk[it & 1];
-    if (chunk >= n_chunks) break;                                 // block-uniform
-    if (threadIdx.x == 0) s_chunk[(it + 1) & 1] = atomicAdd(&m.ctr[6], 1);
-    const int64_t base = (int64_t)chunk * kBatchRows;
-    int32_t key[R];
-    unsigned int old[R];
+    for (int r0 = 0; r0 < per_block; r0 += 4 * 256) {
+      int32_t key[4], slot[4];
+      unsigned int old[4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int64_t t = base + r * 256 + threadIdx.x;
-      key[r] = t < n_touched ? m.fkeys[t] : -1;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      old[r] = seq;
-      if (key[r] >= 0) old[r] = atomicExch(reinterpret_cast<unsigned int*>(ft_entry(m, key[r], kCellWords - 1)), seq);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (old[r] != seq) {
-        s_lead[atomicAdd(&s_n[it & 1], 1)] = key[r];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + key[r]));      // the winner's thread reads it next
+      for (int r = 0; r < 4; ++r) {
+        const int64_t t = base + r0 + r * 256 + threadIdx.x;
+        key[r] = (r0 + r * 256 < per_block && t < n_touched) ? m.fkeys[t] : -1;
       }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        old[r] = seq;
+        if (key[r] >= 0) old[r] = atomicExch(reinterpret_cast<unsigned int*>(ft_entry(m, key[r], kCellWords - 1)), seq);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) slot[r] = old[r] != seq ? m.table[key[r]] : -1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (old[r] != seq) {
+          const int at = atomicAdd(&s_n, 1);
+          s_lead[at] = key[r];
+          s_slot[at] = slot[r];
+          if (slot[r] >= 0) {                                     // the stored voxel: pull its lines into L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.feats + (size_t)slot[r] * kFeat));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(m.weights + slot[r]));
+          }
+        }
+    }
     __syncthreads();
-    const int n_lead = s_n[it & 1];
-    for (int i = threadIdx.x; i < n_lead; i += 256) integrated += finalize_batch_voxel<F32>(m, min_pts, s_lead[i]);
+    const int n_lead = s_n;
+    for (int i = threadIdx.x; i < n_lead; i += 256) integrated += finalize_batch_voxel<F32>(m, min_pts, s_lead[i], s_slot[i]);
   }
   return integrated;
 }
@@ -294,7 +320,6 @@ __device__ __forceinline__ void finalize_publish(const MapDev& m, int integrated
     m.ctr[1] = 0;
     m.ctr[3] = 0;
     m.ctr[4] = 0;
-    m.ctr[6] = 0;                                                 // chunk counter of finalize_batch_rows
   }
 }
 

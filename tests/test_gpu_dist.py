@@ -29,7 +29,7 @@ def _setup(dev):
     return m
 
 
-def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
+def _worker(rank, world, port, out_dir, mode, exchange="nccl", batch=0):
     import torch.distributed as dist
     from bnv_fusion_b200 import synth, config
     config.set_mlp_mode(mode)
@@ -41,14 +41,18 @@ def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
     model = _setup(dev)
     spec = synth.stream_spec("lounge")
-    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21)
+    vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, pool_capacity=1 << 21, frame_batch=batch)
     shard = TileShardedFusion(vol, model, rank, world, brick_log2=4, exchange=exchange, exchange_every=3)
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     rows = 0
-    for fi in range(N_FRAMES):
-        d, K, T = synth.make_frame(spec, fi, seed=2)
-        dd = torch.from_numpy(d.view(np.int16)).to(dev).view(torch.uint16)
-        shard.fuse_depth_frame(dd, K, T, spec.max_depth, stats=stats)
+    fr = [synth.make_frame(spec, fi, seed=2) for fi in range(N_FRAMES)]
+    dd = [torch.from_numpy(d.view(np.int16)).to(dev).view(torch.uint16) for d, _, _ in fr]
+    if batch:                                   # frames 0..batch-1 in one bnv_fuse_frames call, the rest one by one
+        shard.fuse_depth_frames(dd[:batch], np.stack([K for _, K, _ in fr[:batch]]), np.stack([T for _, _, T in fr[:batch]]),
+                                spec.max_depth, stats=stats)
+        rows += int(stats[1])
+    for fi in range(batch, N_FRAMES):
+        shard.fuse_depth_frame(dd[fi], fr[fi][1], fr[fi][2], spec.max_depth, stats=stats)
         rows += int(stats[1])
     vol.check_status()
     coords, feats, weights, _ = vol.to_tensor()
@@ -65,19 +69,20 @@ def _worker(rank, world, port, out_dir, mode, exchange="nccl"):
 EXCHANGES = ["nccl", "p2p"]
 
 
+@pytest.mark.parametrize("batch", [0, 3])
 @pytest.mark.parametrize("exchange", EXCHANGES)
 @pytest.mark.parametrize("mode", ["fp32", "tc16"])
-def test_two_gpu_tile_shard(tmp_path, mode, exchange):
+def test_two_gpu_tile_shard(tmp_path, mode, exchange, batch):
     """fp32 mode (order-independent fixed-point sums): owned + halo values bit-identical to one GPU.
     tc16 mode (fp32 `red.add` partial sums, arrival order differs between runs): same voxels, values to
-    summation-order noise."""
+    summation-order noise.  batch = 3: the first three frames go through ONE sharded bnv_fuse_frames call."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     from bnv_fusion_b200 import synth, config
     from bnv_fusion_b200.volume import SparseVolume
     world = 2
-    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path), mode, exchange), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29600 + os.getpid() % 1000, str(tmp_path), mode, exchange, batch), nprocs=world, join=True)
     config.set_mlp_mode(mode)
     exact = mode == "fp32"
 
