@@ -111,26 +111,35 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     const int u = u0 + lane, v = v0 + warp;
     pix = v * src.cam.W + u;
     bool foreign = false;
-    if (u < src.cam.W && v < src.cam.H && !(dbg & 4)) {
-      if (g.world > 1) {
-        // Tile shard: every rank sees every pixel, but only ~1/world of them land in its bricks.  A float32 estimate
-        // of the point (error ~1e-4 voxel) is enough to tell when the whole 2 x 2 x 2 corner block, padded by a full
-        // voxel, lies inside ONE brick of another rank: the float64 back-projection is skipped for those pixels.
-        const float zf = (float)tile.z[warp + 1][lane + 1];
-        if (zf > 0.f) {
-          const float xf = (float)tile.ax[lane + 1] * zf, yf = (float)tile.ay[warp + 1] * zf;
-          int lo[3], hi[3];
+    const bool in_img = u < src.cam.W && v < src.cam.H && !(dbg & 4);
+    if (g.world > 1) {
+      // Tile shard: every rank sees every pixel, but only ~1/world of them land in its bricks.  A float32 estimate
+      // of the point (error ~1e-4 voxel) is enough to tell when the whole 2 x 2 x 2 corner block, padded by a full
+      // voxel, lies inside ONE brick of another rank: the float64 back-projection is skipped for those pixels, and a
+      // tile without any other pixel (a 32 x 8 pixel tile is smaller than a brick: most tiles of most ranks) is done
+      // after counting its valid pixels for the frame statistics.
+      const float zf = in_img ? (float)tile.z[warp + 1][lane + 1] : 0.f;
+      if (zf > 0.f) {
+        const float xf = (float)tile.ax[lane + 1] * zf, yf = (float)tile.ay[warp + 1] * zf;
+        int lo[3], hi[3];
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const float w = src.cam.T[r * 4] * xf + src.cam.T[r * 4 + 1] * yf + src.cam.T[r * 4 + 2] * zf + src.cam.T[r * 4 + 3];
-            const float cv = (w - g.bmin[r]) * g.inv_vs;
-            lo[r] = (int)floorf(cv - 1.05f) >> g.brick_log2;
-            hi[r] = (int)floorf(cv + 2.05f) >> g.brick_log2;
-          }
-          foreign = lo[0] == hi[0] && lo[1] == hi[1] && lo[2] == hi[2] && (lo[0] + lo[1] + lo[2]) % g.world != g.rank &&
-                    lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0;
+        for (int r = 0; r < 3; ++r) {
+          const float w = src.cam.T[r * 4] * xf + src.cam.T[r * 4 + 1] * yf + src.cam.T[r * 4 + 2] * zf + src.cam.T[r * 4 + 3];
+          const float cv = (w - g.bmin[r]) * g.inv_vs;
+          lo[r] = (int)floorf(cv - 1.05f) >> g.brick_log2;
+          hi[r] = (int)floorf(cv + 2.05f) >> g.brick_log2;
         }
+        foreign = lo[0] == hi[0] && lo[1] == hi[1] && lo[2] == hi[2] && (lo[0] + lo[1] + lo[2]) % g.world != g.rank &&
+                  lo[0] >= 0 && lo[1] >= 0 && lo[2] >= 0;
       }
+      if (__syncthreads_count(zf > 0.f && !foreign) == 0) {      // block-uniform
+        const int n_valid = __syncthreads_count(zf > 0.f);
+        if (tid == 0 && n_valid && !(dbg & 2))
+          atomicAdd(reinterpret_cast<unsigned long long*>(stats + 0), (unsigned long long)n_valid);
+        return;
+      }
+    }
+    if (in_img) {
       if (foreign) valid = true;                 // a valid pixel (frame statistic) that contributes no row here
       else valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
     }
