@@ -274,6 +274,71 @@ def shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, brick
     return out
 
 
+def make_rays(spec, frame, n_rays, rng):
+    """synthetic rays of one view in the shape NeuralMap.optimize feeds calculate_loss (run_e2e.py:119-146): n_rays
+    interior pixels, their world points and 3 x 3 neighbour points"""
+    import torch
+    d, K, T = frame
+    h, w = d.shape
+    z = d.astype(np.float64) / 1000.0
+    valid = (z > 0) & (z < spec.max_depth)
+    v, u = np.mgrid[0:h, 0:w]
+    pc = np.stack([(u - K[0, 2]) / K[0, 0] * z, (v - K[1, 2]) / K[1, 1] * z, z], -1)
+    pw = pc @ np.asarray(T, np.float64)[:3, :3].T + np.asarray(T, np.float64)[:3, 3]
+    inner = np.zeros_like(valid)
+    inner[1:-1, 1:-1] = valid[1:-1, 1:-1]
+    idx = rng.permutation(np.flatnonzero(inner))[:n_rays]
+    vv, uu = idx // w, idx % w
+    off = np.array([[a, b] for a in (-1, 0, 1) for b in (-1, 0, 1)])
+    nv, nu = vv[:, None] + off[None, :, 0], uu[:, None] + off[None, :, 1]
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return {"uv": f32(np.stack([uu, vv], -1))[None], "gt_pts": f32(pw[vv, uu])[None], "mask": torch.ones(1, len(idx)),
+            "neighbor_pts": f32(pw[nv, nu])[None], "neighbor_masks": f32(valid[nv, nu])[None],
+            "T_wc": f32(T)[None], "intr_mat": f32(K)[None]}
+
+
+def optim_iteration(torch, model, vol, spec, frames, dev, iters=10):
+    """One iteration of NeuralMap.optimize (run_e2e.py:111-156) at the reference's configured shape: 5 000 rays of one
+    view in 5 splits of 1 000 (configs/dataset/fusion_inference_dataset.yaml:8, configs/model/fusion_pointnet_model.yaml:7),
+    35 samples per ray, loss + backward per split, one Adam step on volume.features.  Extra key, not the headline."""
+    from bnv_fusion_b200.render import calculate_loss
+    rng = np.random.default_rng(0)
+    views = [{k: t.to(dev) for k, t in make_rays(spec, frames[i], 5000, rng).items()} for i in range(4)]
+    keep = vol.features
+    vol.features = torch.nn.Parameter(vol.features.clone())
+    opt = torch.optim.Adam([vol.features], lr=0.001)
+    td = min(10 * spec.voxel_size * 0.5, 0.1)
+
+    def iteration(i):
+        rays = views[i % len(views)]
+        opt.zero_grad()
+        n = rays["uv"].shape[1]
+        for s0 in range(0, n, 1000):
+            sl = slice(s0, min(s0 + 1000, n))
+            part = {k: (t if k in ("T_wc", "intr_mat") else t[:, sl]) for k, t in rays.items()}
+            calculate_loss(vol, part, model.nerf, truncated_units=10, truncated_dist=td, ray_max_dist=3)["depth_bce_loss"].backward()
+        opt.step()
+        return n
+
+    for i in range(3):
+        n = iteration(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(iters):
+        iteration(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / iters
+    ms = e0.elapsed_time(e1) / iters
+    vol.features = keep
+    return {"ms_per_iteration": ms, "host_wall_ms_per_iteration": wall_ms, "rays": n, "samples_per_ray": 35, "splits": 5,
+            "queries_per_s": n * 35 / (ms * 1e-3),
+            "what": "NeuralMap.optimize iteration: 5 x (ray samples, count_optim, decode, SDF loss, decode backward) + Adam step; "
+                    "the backward runs on the fp32 CUDA cores"}
+
+
 def single_frame_calls(torch, model, spec, frames, devf, host, dev, flush, steps):
     """The one-call-per-frame form (bnv_fuse_frame / bnv_fuse_frame_host, what an unchanged run_e2e.py loop issues) on a
     map of its own with the single-frame table layout: cold device-resident frames/s and host-buffer frames/s."""
@@ -558,6 +623,9 @@ def run_b200(args):
     parity = None
     if world > 1 and not args.no_parity:
         parity = shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, args.brick_log2, args.exchange, batch=B)
+    optim = None
+    if world == 1 and not args.no_optim:
+        optim = optim_iteration(torch, model, vol, spec, frames, dev)
     n_q_job, dec_ms_job = n_q, dec_ms
     if world > 1:      # whole-job decode: every rank decodes its own voxels; halo copies do not count
         own = int(shard.owned_rows().sum())
@@ -615,21 +683,26 @@ def run_b200(args):
                          "bound": "tensor",
                          "achieved": enc_tflops, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                          "frac": enc_tflops / pk["tf_burst"],
-                         "traffic": traffic("encode_ws_kernel" if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
+                         # ncu dram bytes per launch: captured for one frame per launch and for 7 frames per launch
+                         "traffic": traffic(("encode_ws_kernel" if B == 1 else "encode_ws_kernel_batch7" if B == 7 else "-")
+                                            if config.mlp_mode_name() == "tc16" else "encode_rows_simt_kernel"),
                          "peak_source": pk["src"],
                          "rows_per_launch": rows_per_launch, "kernel_ms": enc_avg, "prepass_ms": pre_avg, "finalize_ms": fin_avg,
                          "timing": "CUDA events around every kernel over a second pass of the same K cold steps "
                                    "(ms_per_step_with_kernel_events); each event-bracketed kernel reads ~3-5 us long"},
             # the scatter stage is "HBM-bound by contract": the prepass (depth in, claims + counts, point
             # records out) and finalize (scratch rows in, map upsert) kernels carry all of the frame's algorithmic bytes
-            "roofline_hbm": {"kernel": "frame_prepass_kernel + finalize_fused_kernel (scatter / upsert stage)", "bound": "hbm",
+            "roofline_hbm": {"kernel": ("frame_prepass_kernel + finalize_fused_kernel" if B == 1 else
+                                        "frame_prepass_batch_kernel + finalize_batch_kernel") + " (scatter / upsert stage)", "bound": "hbm",
                              "achieved": scatter_bytes / ((pre_avg + fin_avg) * 1e-3) / 1e9,
                              "peak": pk["hbm_gbs"], "unit": "GB/s",
                              "frac": scatter_bytes / ((pre_avg + fin_avg) * 1e-3) / 1e9 / pk["hbm_gbs"],
                              "algorithmic_bytes_per_launch": scatter_bytes,
-                             "traffic": ((traffic("frame_prepass_kernel") or 0) + (traffic("finalize_fused_kernel") or 0)) or None,
-                             "note": "bytes = 2*H*W (uint16 depth) + 64 + M_t*44 + M*80 (SURVEY 8d with the uint16 depth "
-                                     "image this path reads); M_t, M from the frame statistics; time = prepass + finalize"},
+                             "traffic": (((traffic("frame_prepass_kernel") or 0) + (traffic("finalize_fused_kernel") or 0)) if B == 1 else
+                                         ((traffic("frame_prepass_batch_kernel") or 0) + (traffic("finalize_batch_kernel") or 0)) if B == 7
+                                         else 0) or None,
+                             "note": "bytes = frames_per_step * (2*H*W (uint16 depth) + 64) + M_t*44 + M*80 (SURVEY 8d with the uint16 "
+                                     "depth image this path reads); M_t, M from the step's statistics; time = prepass + finalize"},
             "decode": {"value": n_q_job / (dec_ms_job * 1e-3) / 1e6, "unit": "Mqueries/s", "queries": n_q_job,
                        "active_voxels_rank0": A, "ms": dec_ms_job,
                        "path": "bnv_decode_voxel_blocks (meshlize samples): G[voxel][offset] table on the tensor cores + blend",
@@ -654,6 +727,8 @@ def run_b200(args):
         }
         if single is not None:
             out["single_frame_calls"] = single
+        if optim is not None:
+            out["optim_iteration"] = optim
         if parity is not None:
             out["shard_parity"] = parity
         print(json.dumps(out))
@@ -857,6 +932,7 @@ def main():
     ap.add_argument("--frame-batch", type=int, default=7,
                     help="frames per step = per bnv_fuse_frames call (1: one bnv_fuse_frame call per frame)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-optim", action="store_true", help="skip the optimisation-iteration extra")
     ap.add_argument("--ref-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-unsharded map comparison")
     ap.add_argument("--paced-fps", type=float, default=0.0,

@@ -1,5 +1,5 @@
-"""Short workload for ncu captures: 6 fused lounge frames, one decode_pts over every active voxel's 27
-samples, one factored block decode, one TSDF integration (see tools/gpu_profile.sh)."""
+"""Short workload for ncu captures: 6 fused lounge frames (one call each), two 7-frame batches, one decode_pts over
+every active voxel's 27 samples, one factored block decode, one TSDF integration (see tools/gpu_profile.sh)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,6 +20,13 @@ frames = [synth.make_frame(spec, i, seed=0) for i in range(6)]
 dd = [torch.from_numpy(d.view(np.int16)).to(dev).view(torch.uint16) for d, _, _ in frames]
 for i in range(6):
     m.fuse_depth_frame(vol, dd[i], frames[i][1], frames[i][2], spec.max_depth)
+volb = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, frame_batch=7)
+fb = [synth.make_frame(spec, i, seed=0) for i in range(14)]
+db = [torch.from_numpy(d.view(np.int16)).to(dev).view(torch.uint16) for d, _, _ in fb]
+for b0 in (0, 7):
+    m.fuse_depth_frames(volb, db[b0:b0 + 7], np.stack([K for _, K, _ in fb[b0:b0 + 7]]), np.stack([T for _, _, T in fb[b0:b0 + 7]]),
+                        spec.max_depth)
+volb.check_status()
 vol.to_tensor()
 vol.weights += 8.0
 A = vol.active_coordinates.shape[0]
