@@ -623,6 +623,31 @@ def run_b200(args):
     parity = None
     if world > 1 and not args.no_parity:
         parity = shard_parity_check(dist, torch, model, spec, frames, dev, rank, world, args.brick_log2, args.exchange, batch=B)
+    # ---- BASELINE configs[3]: mesh extraction = SDF decode of the 27 samples of every active voxel + marching cubes ----
+    mesh = None
+    if world == 1:
+        def timed(fn, n=3):
+            ts = []
+            for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                out = fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts)), out
+        t_dec, blocks = timed(lambda: vol.decode_voxel_blocks(model.nerf))
+        t_mc, (mv, mf) = timed(lambda: vol.extract_triangles(blocks, weld=False))
+        t_weld, (wv, wf) = timed(lambda: vol.extract_triangles(blocks, weld=True))
+        t0 = time.perf_counter()
+        res = vol.meshlize(model.nerf)
+        t_all = (time.perf_counter() - t0) * 1e3
+        mesh = {"active_voxels": A, "queries": A * 27, "triangles": int(mf.shape[0]), "welded_vertices": int(wv.shape[0]),
+                "decode_ms": t_dec, "marching_cubes_ms": t_mc, "marching_cubes_welded_ms": t_weld,
+                "decode_plus_mc_Mqueries_per_s": A * 27 / ((t_dec + t_mc) * 1e-3) / 1e6,
+                "meshlize_call_ms_incl_host_copy": t_all, "returned_mesh": res is not None,
+                "what": "SparseVolume.meshlize on the fused map: bnv_decode_voxel_blocks + bnv_mesh_count / bnv_mesh_emit "
+                        "(sparse_volume.py:697-766: 500-voxel decode batches + one skimage marching-cubes call per voxel on the CPU)"}
     optim = None
     if world == 1 and not args.no_optim:
         optim = optim_iteration(torch, model, vol, spec, frames, dev)
@@ -729,6 +754,8 @@ def run_b200(args):
             out["single_frame_calls"] = single
         if optim is not None:
             out["optim_iteration"] = optim
+        if mesh is not None:
+            out["mesh_extraction"] = mesh
         if parity is not None:
             out["shard_parity"] = parity
         print(json.dumps(out))

@@ -53,6 +53,26 @@ class _RayLossFn(torch.autograd.Function):
         return (None if ctx.grad is None else ctx.grad * g,) + (None,) * 10
 
 
+_CAM_CACHE = {}
+
+
+def _camera_host(rays):
+    """K [9] and T_wc [16] as host float32 arrays.  NeuralMap.optimize passes the same (CUDA) camera tensors with every
+    ray split of a view (run_e2e.py:127-139): the device-to-host read -- a stream synchronisation -- happens once per
+    tensor version, not once per call."""
+    Kt, Tt = rays["intr_mat"], rays["T_wc"]
+    key = (Kt.data_ptr(), Kt._version, Tt.data_ptr(), Tt._version, str(Kt.device))
+    hit = _CAM_CACHE.get(key)
+    if hit is None:
+        K = np.ascontiguousarray(Kt.reshape(-1, 3, 3)[0].detach().cpu().numpy().astype(np.float32).reshape(9))
+        T = np.ascontiguousarray(Tt.reshape(-1, 4, 4)[0].detach().cpu().numpy().astype(np.float32).reshape(16))
+        if len(_CAM_CACHE) > 64:
+            _CAM_CACHE.clear()
+        # the tensors are kept alive with the entry, so their addresses cannot be recycled while it is cached
+        hit = _CAM_CACHE[key] = (K, T, Kt, Tt)
+    return hit[0], hit[1]
+
+
 def sample_rays(volume, rays, truncated_units, truncated_dist, ray_max_dist, t_rand=None):
     """get_camera_params + hierarchical_sampling of render_with_rays (render_utils.py:461-492): world points on the rays
     [n, S, 3] with S = 2 * truncated_units fine + int(5 * ray_max_dist) coarse samples per ray (fine first, unsorted).
@@ -67,8 +87,7 @@ def sample_rays(volume, rays, truncated_units, truncated_dist, ray_max_dist, t_r
         t_rand = (torch.rand(n, n_fine, device=dev), torch.rand(n, n_coarse, device=dev))
     tf = t_rand[0].reshape(n, n_fine).to(dev).float().contiguous()
     tc = t_rand[1].reshape(n, n_coarse).to(dev).float().contiguous()
-    K = np.ascontiguousarray(rays["intr_mat"].reshape(-1, 3, 3)[0].detach().cpu().numpy().astype(np.float32).reshape(9))
-    T = np.ascontiguousarray(rays["T_wc"].reshape(-1, 4, 4)[0].detach().cpu().numpy().astype(np.float32).reshape(16))
+    K, T = _camera_host(rays)
     pts = torch.empty((n, n_fine + n_coarse, 3), dtype=torch.float32, device=dev)
     _lib.check(lib.bnv_ray_samples(_lib.ptr(uv), _lib.ptr(gt), n, _lib.ptr(K), _lib.ptr(T), _lib.ptr(tf), n_fine, _lib.ptr(tc),
                                    n_coarse, float(truncated_dist), _lib.ptr(pts), volume._stream()), "bnv_ray_samples")

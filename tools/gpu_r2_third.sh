@@ -8,6 +8,7 @@ import json
 d=json.loads(open("gpurun_out/chk_bench_b200.json").read().strip().splitlines()[-1])
 r=d["roofline"]
 print("B", d["config"]["frames_per_step"], "single", {k: (round(v) if isinstance(v, float) else v) for k, v in (d.get("single_frame_calls") or {}).items() if k != "what"})
+print("mesh", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in (d.get("mesh_extraction") or {}).items() if k != "what"})
 print("optim", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in (d.get("optim_iteration") or {}).items() if k != "what"})
 print("fps", round(d["value"]), "warm", round(d["value_warm"]), "e2e", round(d["e2e"]["value"]), "pre_ms", round(r["prepass_ms"],4), "enc_ms", round(r["kernel_ms"],4),
       "fin_ms", round(r["finalize_ms"],4), "enc_frac", round(r["frac"],3), "hbm_frac", round(d["roofline_hbm"]["frac"],3),
