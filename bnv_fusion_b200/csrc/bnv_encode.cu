@@ -71,20 +71,105 @@ constexpr int kPreThreads = kTileW * kTileH;   // 256: one 32 x 8 pixel tile (a 
 // L2 are in flight before the first result is read; only the last one is predicated.  (Padding with no-op atomics on
 // a dummy word, as this kernel first did, doubled the atomic traffic -- profiles/r2e.)
 // Returns the mask of pairs whose voxel this thread touched first (count was 0).
+// A pair = (flat voxel id, run length | frame << 8).
+__device__ __forceinline__ int pair_frame(const int2& pr) { return pr.y >> 8; }
+__device__ __forceinline__ unsigned int pair_run(const int2& pr) { return (unsigned int)(pr.y & 0xff); }
+
 template <int NP>
-__device__ __forceinline__ uint32_t claim_pairs(const MapDev& m, int frame, const int2 (&pr)[8]) {
+__device__ __forceinline__ uint32_t claim_pairs(const MapDev& m, const int2 (&pr)[8]) {
   unsigned int old[NP];
 #pragma unroll
   for (int j = 0; j < NP - 1; ++j)
-    old[j] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[j].x, frame)), (unsigned int)pr[j].y);
+    old[j] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[j].x, pair_frame(pr[j]))), pair_run(pr[j]));
   old[NP - 1] = 1u;
   if (pr[NP - 1].x >= 0)
-    old[NP - 1] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[NP - 1].x, frame)), (unsigned int)pr[NP - 1].y);
+    old[NP - 1] = atomicAdd(reinterpret_cast<unsigned int*>(ft_entry(m, pr[NP - 1].x, pair_frame(pr[NP - 1]))), pair_run(pr[NP - 1]));
   uint32_t win = 0;
 #pragma unroll
   for (int j = 0; j < NP; ++j)
     if (old[j] == 0u) win |= 1u << j;
   return win;
+}
+
+// Warp-level claim + count of 32 points (one per lane; `own` == 0: no point): runs of lanes with the same 2 x 2 x 2
+// corner block -> (key, run length) pairs per owned corner, compacted into the warp's shared-memory list, then claimed
+// with dense independent atomics.  Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE
+// atomicAdd of its length per corner.  Two points share the voxel of one corner exactly when they share all eight (same
+// floor voxel, same ceil - floor pattern), so the runs are found once per point, not once per corner.  (Issued in place
+// under `if (head)`, the compiler sinks each result test into its branch: eight serialised L2 round trips per thread,
+// 55 % of the prepass' stall samples in profiles/r2a.)
+// Returns the mask of this lane's pairs (pr) whose voxel it touched first.
+__device__ __forceinline__ uint32_t claim_points(const MapDev& m, int2* __restrict__ runs, int lane, int fx, int fy, int fz, int ex,
+                                                 int ey, int ez, uint32_t own, int frame, bool sharded, bool no_claims,
+                                                 int2 (&pr)[8]) {
+  const GeomDev& g = m.g;
+  const int32_t key0 = own ? fx * g.nyz + fy * g.n[2] + fz : -1 - lane;   // rule A5 (int32); negatives never merge
+  const int32_t pat = ex | (ey << 1) | (ez << 2) | (frame << 3);
+  const int32_t prev_key = __shfl_up_sync(0xffffffffu, key0, 1), prev_pat = __shfl_up_sync(0xffffffffu, pat, 1);
+  const bool head = lane == 0 || prev_key != key0 || prev_pat != pat;
+  const uint32_t heads = __ballot_sync(0xffffffffu, head);
+  const bool lead = head && own != 0;                                    // this lane writes its run's pairs
+  int n_runs, at;                                                        // pairs of the warp (uniform) / before this lane
+  if (!sharded) {
+    const uint32_t real = __ballot_sync(0xffffffffu, lead);
+    at = 8 * __popc(real & ((1u << lane) - 1u));
+    n_runs = 8 * __popc(real);
+  } else {
+    const int mine = lead ? __popc(own) : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    at = incl - mine;
+    n_runs = __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lead) {
+    const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
+    const int run = (rest ? __ffs(rest) : 32 - lane) | (frame << 8);
+    const int dx = ex * g.nyz, dy = ey * g.n[2];
+    int2* out = runs + at;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)                                          // rule A3 corner order (modules.py:178-247)
+      if ((own >> k) & 1u)
+        *out++ = make_int2(key0 + (corner_sx(k) ? dx : 0) + (corner_sy(k) ? dy : 0) + (corner_sz(k) ? ez : 0), run);
+  }
+  __syncwarp();
+  // lane j takes the warp's pairs j, j + 32, ...
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = j * 32 + lane;
+    pr[j] = i < n_runs ? runs[i] : make_int2(-1, 0);
+  }
+  __syncwarp();
+  uint32_t win = 0;
+  switch (no_claims ? 0 : (n_runs + 31) >> 5) {                          // warp-uniform
+    case 1: win = claim_pairs<1>(m, pr); break;
+    case 2: win = claim_pairs<2>(m, pr); break;
+    case 3: win = claim_pairs<3>(m, pr); break;
+    case 4: win = claim_pairs<4>(m, pr); break;
+    case 5: win = claim_pairs<5>(m, pr); break;
+    case 6: win = claim_pairs<6>(m, pr); break;
+    case 7: win = claim_pairs<7>(m, pr); break;
+    case 8: win = claim_pairs<8>(m, pr); break;
+    default: break;
+  }
+  return win;
+}
+
+// first touchers publish their dense scratch rows (first row = `row`)
+__device__ __forceinline__ void publish_rows(const MapDev& m, const int2 (&pr)[8], uint32_t win, int row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if ((win >> j) & 1u) {
+      // the dense row in the entry's high word (visible to the kernels that follow) and its key
+      reinterpret_cast<int32_t*>(ft_entry(m, pr[j].x, pair_frame(pr[j])))[1] = row;
+      m.fkeys[row] = pr[j].x;
+      // finalize will look this voxel up in the persistent table two kernels from now: pull the line into L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + pr[j].x));
+      ++row;
+    }
 }
 
 // `frame` = position of the frame in its batch (0 for a single frame): selects the frame's word of every table entry
@@ -169,19 +254,9 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     fl[a] = floorf(c[a]);
     ce[a] = ceilf(c[a]);
   }
-  // ---- runs of lanes with the same 2 x 2 x 2 corner block -> (key, run length) pairs per owned corner, compacted per
-  // warp.  Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE atomicAdd of its length per
-  // corner.  Two pixels share the voxel of one corner exactly when they share all eight (same floor voxel, same
-  // ceil - floor pattern), so the runs are found once per pixel, not once per corner.  The pairs go to a per-warp
-  // shared-memory list first, so that the atomics are issued by dense, independent instructions (lane j takes pairs
-  // j, j + 32, ...): all of a lane's round trips to L2 are in flight together.  (Issued in place under `if (head)`, the
-  // compiler sinks each result test into its branch: eight serialised L2 round trips per thread, 55 % of this kernel's
-  // stall samples in profiles/r2a.)
   const bool sharded = g.world > 1;                                      // block-uniform
   const int fx = (int)fl[0], fy = (int)fl[1], fz = (int)fl[2];
   const int ex = (int)ce[0] - fx, ey = (int)ce[1] - fy, ez = (int)ce[2] - fz;          // 0 or 1 each
-  const int32_t key0 = inb ? fx * g.nyz + fy * g.n[2] + fz : -1 - lane;  // rule A5 (int32); negatives never merge
-  const int32_t pat = ex | (ey << 1) | (ez << 2);
   uint32_t own = inb ? 0xffu : 0u;
   if (sharded && inb) {
     own = 0;
@@ -189,59 +264,12 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     for (int k = 0; k < 8; ++k)                                          // rule A3 corner order (modules.py:178-247)
       own |= (owner_of(g, fx + (corner_sx(k) ? ex : 0), fy + (corner_sy(k) ? ey : 0), fz + (corner_sz(k) ? ez : 0)) == g.rank ? 1u : 0u) << k;
   }
-  const int32_t prev_key = __shfl_up_sync(0xffffffffu, key0, 1), prev_pat = __shfl_up_sync(0xffffffffu, pat, 1);
-  const bool head = lane == 0 || prev_key != key0 || prev_pat != pat;
-  const uint32_t heads = __ballot_sync(0xffffffffu, head);
-  const bool lead = head && own != 0;                                    // this lane writes its run's pairs
-  int n_runs, at;                                                        // pairs of the warp (uniform) / before this lane
-  if (!sharded) {
-    const uint32_t real = __ballot_sync(0xffffffffu, lead);
-    at = 8 * __popc(real & ((1u << lane) - 1u));
-    n_runs = 8 * __popc(real);
-  } else {
-    const int mine = lead ? __popc(own) : 0;
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    at = incl - mine;
-    n_runs = __shfl_sync(0xffffffffu, incl, 31);
-  }
-  if (lead) {
-    const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
-    const int run = rest ? __ffs(rest) : 32 - lane;
-    const int dx = ex * g.nyz, dy = ey * g.n[2];
-    int2* out = s_runs[warp] + at;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if ((own >> k) & 1u)
-        *out++ = make_int2(key0 + (corner_sx(k) ? dx : 0) + (corner_sy(k) ? dy : 0) + (corner_sz(k) ? ez : 0), run);
-  }
-  __syncwarp();
-  // ---- claim + count: lane j takes the warp's pairs j, j + 32, ... ----
-  // (Merging the tile's pairs per voxel in a shared-memory hash table first -- ~6 x fewer global atomics -- was tried
-  // in round 2: 148 instead of 153 us on 7 frames, 31 instead of 27 us on one; the claims cost a round trip per block,
-  // not a share of the atomic throughput.)
+  // ---- claim + count.  Tried and removed (round 2): merging the tile's pairs per voxel in a
+  // shared-memory hash table first (~6 x fewer global atomics: 148 instead of 153 us on 7 frames, 31 instead of 27 us
+  // on one); leaving the claims to a second kernel over the compacted point records (195 instead of 156 us, 36 instead
+  // of 27 us: the claims cost the same ~100 G atomics/s there, plus the records' second trip through L2) ----
   int2 pr[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int i = j * 32 + lane;
-    pr[j] = i < n_runs ? s_runs[warp][i] : make_int2(-1, 0);
-  }
-  uint32_t win = 0;
-  switch ((dbg & 1) ? 0 : (n_runs + 31) >> 5) {                        // warp-uniform
-    case 1: win = claim_pairs<1>(m, frame, pr); break;
-    case 2: win = claim_pairs<2>(m, frame, pr); break;
-    case 3: win = claim_pairs<3>(m, frame, pr); break;
-    case 4: win = claim_pairs<4>(m, frame, pr); break;
-    case 5: win = claim_pairs<5>(m, frame, pr); break;
-    case 6: win = claim_pairs<6>(m, frame, pr); break;
-    case 7: win = claim_pairs<7>(m, frame, pr); break;
-    case 8: win = claim_pairs<8>(m, frame, pr); break;
-    default: break;
-  }
+  const uint32_t win = claim_points(m, s_runs[warp], lane, fx, fy, fz, ex, ey, ez, own, frame, sharded, (dbg & 1) != 0, pr);
   // ---- first touchers allocate dense scratch rows; in-bounds points get a record slot ---------------------
   const int n_new = __popc(win);
   int incl = n_new;
@@ -285,16 +313,7 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     row += s_new[w];
     rec += s_keep[w];
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if ((win >> j) & 1u) {
-      // publish the dense row in the entry's high word (visible to the kernels that follow) and its key
-      reinterpret_cast<int32_t*>(ft_entry(m, pr[j].x, frame))[1] = row;
-      m.fkeys[row] = pr[j].x;
-      // finalize will look this voxel up in the persistent table two kernels from now: pull the line into L2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(m.table + pr[j].x));
-      ++row;
-    }
+  publish_rows(m, pr, win, row);
   if (keep && !(dbg & 8)) {
     float4* r4 = reinterpret_cast<float4*>(m.prec + (size_t)rec * 8);
     r4[0] = make_float4(c[0], c[1], c[2], p[3]);
@@ -304,7 +323,7 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
 }
 
 template <bool FROM_DEPTH>
-__global__ void __launch_bounds__(kPreThreads) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
+__global__ void __launch_bounds__(kPreThreads, 5) frame_prepass_kernel(MapDev m, EncSrc src, long long* __restrict__ stats, int dbg) {
   prepass_body<FROM_DEPTH>(m, src, 0, stats, dbg);
 }
 
@@ -572,14 +591,10 @@ static int launch_encode(bnv_map_t* map, const EncSrc& src, bool from_depth, int
     return BNV_E_CAPACITY;
   }
   if (n_threads == 0) return BNV_OK;
-  if (from_depth) {
-    const unsigned tiles = (unsigned)(((src.cam.W + kTileW - 1) / kTileW) * ((src.cam.H + kTileH - 1) / kTileH));
-    BNV_CUDA(launch_pdl(frame_prepass_kernel<true>, dim3(tiles), dim3(kPreThreads), 0, s, map->d, src, (long long*)map->stats,
-                        g_prepass_debug));
-  } else {
-    BNV_CUDA(launch_pdl(frame_prepass_kernel<false>, dim3((unsigned)((n_threads + kPreThreads - 1) / kPreThreads)),
-                        dim3(kPreThreads), 0, s, map->d, src, (long long*)map->stats, g_prepass_debug));
-  }
+  const dim3 grid(from_depth ? (unsigned)(((src.cam.W + kTileW - 1) / kTileW) * ((src.cam.H + kTileH - 1) / kTileH))
+                             : (unsigned)((n_threads + kPreThreads - 1) / kPreThreads));
+  BNV_CUDA(launch_pdl(from_depth ? frame_prepass_kernel<true> : frame_prepass_kernel<false>, grid, dim3(kPreThreads), 0, s, map->d,
+                      src, (long long*)map->stats, g_prepass_debug));
   BNV_LAUNCH_CHECK("frame_prepass_kernel");
   return launch_encode_rows(map, n_threads, enc, mode, s);
 }
