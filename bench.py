@@ -453,6 +453,14 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if shard is not None:
+        # set-up, not warm-up: two exchange epochs, so that both double-buffered all-gather buffer pairs have been through
+        # NCCL once before anything is timed (an epoch's first use of a buffer pair inside the timed region cost ~20 % of
+        # an 8-GPU run: profiles/r2f_scaling_breakdown.md, run 2)
+        for i in range(2):
+            step(i)
+            shard.exchange_now()
+        shard.synchronize()
     for i in range(args.warmup):
         step(i)
     barrier()
