@@ -91,11 +91,11 @@ __device__ __forceinline__ uint32_t claim_pairs(const MapDev& m, const int2 (&pr
   return win;
 }
 
-// Warp-level claim + count of 32 points (one per lane; `own` == 0: no point): runs of lanes with the same 2 x 2 x 2
-// corner block -> (key, run length) pairs per owned corner, compacted into the warp's shared-memory list, then claimed
-// with dense independent atomics.  Neighbouring pixels mostly fall into the same voxel: a run is counted with ONE
-// atomicAdd of its length per corner.  Two points share the voxel of one corner exactly when they share all eight (same
-// floor voxel, same ceil - floor pattern), so the runs are found once per point, not once per corner.  (Issued in place
+// Warp-level claim + count of 32 points (one per lane; `own` == 0: no point): groups of lanes with the same 2 x 2 x 2
+// corner block -> (key, group size) pairs per owned corner, compacted into the warp's shared-memory list, then claimed
+// with dense independent atomics.  Neighbouring pixels mostly fall into the same voxel: a group is counted with ONE
+// atomicAdd of its size per corner.  Two points share the voxel of one corner exactly when they share all eight (same
+// floor voxel, same ceil - floor pattern), so the groups are found once per point (two match.any), not once per corner.  (Issued in place
 // under `if (head)`, the compiler sinks each result test into its branch: eight serialised L2 round trips per thread,
 // 55 % of the prepass' stall samples in profiles/r2a.)
 // Returns the mask of this lane's pairs (pr) whose voxel it touched first.
@@ -105,10 +105,9 @@ __device__ __forceinline__ uint32_t claim_points(const MapDev& m, int2* __restri
   const GeomDev& g = m.g;
   const int32_t key0 = own ? fx * g.nyz + fy * g.n[2] + fz : -1 - lane;   // rule A5 (int32); negatives never merge
   const int32_t pat = ex | (ey << 1) | (ez << 2) | (frame << 3);
-  const int32_t prev_key = __shfl_up_sync(0xffffffffu, key0, 1), prev_pat = __shfl_up_sync(0xffffffffu, pat, 1);
-  const bool head = lane == 0 || prev_key != key0 || prev_pat != pat;
-  const uint32_t heads = __ballot_sync(0xffffffffu, head);
-  const bool lead = head && own != 0;                                    // this lane writes its run's pairs
+  // lanes with the same corner block, wherever they sit in the warp (an 8 x 4 pixel patch in the depth path)
+  const uint32_t group = __match_any_sync(0xffffffffu, key0) & __match_any_sync(0xffffffffu, pat);
+  const bool lead = own != 0 && lane == __ffs(group) - 1;               // this lane writes its group's pairs
   int n_runs, at;                                                        // pairs of the warp (uniform) / before this lane
   if (!sharded) {
     const uint32_t real = __ballot_sync(0xffffffffu, lead);
@@ -126,8 +125,7 @@ __device__ __forceinline__ uint32_t claim_points(const MapDev& m, int2* __restri
     n_runs = __shfl_sync(0xffffffffu, incl, 31);
   }
   if (lead) {
-    const uint32_t rest = lane == 31 ? 0u : heads >> (lane + 1);
-    const int run = (rest ? __ffs(rest) : 32 - lane) | (frame << 8);
+    const int run = __popc(group) | (frame << 8);
     const int dx = ex * g.nyz, dy = ey * g.n[2];
     int2* out = runs + at;
 #pragma unroll
@@ -193,7 +191,10 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     if (!(dbg & 16)) stage_frame_tile(tile, src.depth, src.cam, u0, v0);     // reads the depth image only
     __syncthreads();
     grid_dependency_wait();                                                  // the previous frame's finalize
-    const int u = u0 + lane, v = v0 + warp;
+    // a warp covers an 8 x 4 pixel patch of the tile (not 32 pixels of one image row): the patch is about as wide as it
+    // is high in voxels, so more of its pixels share their corner block and are counted together (claim_points)
+    const int tx = (warp & 3) * 8 + (lane & 7), ty = (warp >> 2) * 4 + (lane >> 3);
+    const int u = u0 + tx, v = v0 + ty;
     pix = v * src.cam.W + u;
     bool foreign = false;
     const bool in_img = u < src.cam.W && v < src.cam.H && !(dbg & 4);
@@ -203,9 +204,9 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
       // voxel, lies inside ONE brick of another rank: the float64 back-projection is skipped for those pixels, and a
       // tile without any other pixel (a 32 x 8 pixel tile is smaller than a brick: most tiles of most ranks) is done
       // after counting its valid pixels for the frame statistics.
-      const float zf = in_img ? (float)tile.z[warp + 1][lane + 1] : 0.f;
+      const float zf = in_img ? (float)tile.z[ty + 1][tx + 1] : 0.f;
       if (zf > 0.f) {
-        const float xf = (float)tile.ax[lane + 1] * zf, yf = (float)tile.ay[warp + 1] * zf;
+        const float xf = (float)tile.ax[tx + 1] * zf, yf = (float)tile.ay[ty + 1] * zf;
         int lo[3], hi[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
@@ -226,7 +227,7 @@ __device__ __forceinline__ void prepass_body(const MapDev& m, const EncSrc& src,
     }
     if (in_img) {
       if (foreign) valid = true;                 // a valid pixel (frame statistic) that contributes no row here
-      else valid = backproject_tile_pixel(tile, src.cam, lane, warp, u, v, p);
+      else valid = backproject_tile_pixel(tile, src.cam, tx, ty, u, v, p);
     }
     if (foreign) {                               // park it outside the bounds: rule A1 drops it below
 #pragma unroll
