@@ -745,6 +745,12 @@ int bnv_fuse_frames(bnv_map_t* map, const uint16_t* const* depth, int n_frames, 
     fb.depth[i] = depth[i];
   }
   cudaStream_t s = (cudaStream_t)stream;
+  // the batch's sequence number = the value its finalize swaps into the cells' lock words.  0 is the cleared word; on
+  // the wrap after 2^32 batches the table (all zero between batches except for old lock words) is cleared once
+  if (++map->batch_seq == 0u) {
+    BNV_CUDA(cudaMemsetAsync(map->d.ftable, 0, ((size_t)map->d.g.n_vox << map->d.fshift) * 8, s));
+    map->batch_seq = 1u;
+  }
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[0], s));
   const unsigned tiles = (unsigned)(((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH));
   BNV_CUDA(launch_pdl(frame_prepass_batch_kernel, dim3(tiles, (unsigned)n_frames), dim3(kPreThreads), 0, s, map->d, fb,
@@ -753,7 +759,6 @@ int bnv_fuse_frames(bnv_map_t* map, const uint16_t* const* depth, int n_frames, 
   rc = launch_encode_rows(map, (int64_t)n_frames * H * W, enc, mode, s);
   if (rc) return rc;
   if (map->timing) BNV_CUDA(cudaEventRecord(map->ev[1], s));
-  if (++map->batch_seq == 0u) map->batch_seq = 1u;     // 0 is the cleared lock word (a wrap after 2^32 batches)
   {
     const dim3 grid(148 * 2), block(256);
     auto kernel = mode == BNV_MLP_TC16 ? finalize_batch_kernel<true> : finalize_batch_kernel<false>;
