@@ -416,6 +416,8 @@ def run_b200(args):
                            "nerf.model.params": torch.from_numpy(p["decoder"])})
     model.eval(); model.cuda(); model.freeze()
     B = max(1, int(args.frame_batch))               # frames per step (one bnv_fuse_frames call); 1: one call per frame
+    if B > 7:
+        raise SystemExit("--frame-batch: bnv_fuse_frames takes at most 7 frames per call")
     vol = SparseVolume(8, spec.voxel_size, spec.dimensions, 8, device=dev, frame_batch=B if B > 1 else 0)
     shard = None
     if world > 1:

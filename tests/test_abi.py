@@ -46,6 +46,24 @@ def test_bad_arguments_fail_loudly_without_gpu():
     assert lib.bnv_map_halo_enable(None, 16) == -1 and lib.bnv_map_halo_pack(None, None, 16, None) == -1
     assert lib.bnv_exchange_push(None, None) == -1 and lib.bnv_exchange_join(None, None) == -1
     assert lib.bnv_exchange_destroy(None) == 0
+    # frame batches: null map / null frame list / out-of-range batch size
+    assert lib.bnv_fuse_frames(None, None, 2, 480, 640, None, None, 3.0, None, 8, 1, None, None, None) == -1
+    assert lib.bnv_fuse_frames_host(None, None, 2, 480, 640, None, None, 3.0, None, 8, 1, None, None, 0, None) == -1
+    assert lib.bnv_map_set_frame_batch(None, 7) == -1 and b"frames per batch" in lib.bnv_last_error()
+
+
+def test_batch_camera_broadcast():
+    """LitFusionPointNet._batch_cameras: one shared K [3,3] or one K per frame; T_wc per frame (host logic of
+    fuse_depth_frames)"""
+    import numpy as np
+    from bnv_fusion_b200.model import LitFusionPointNet
+    K = np.arange(9, dtype=np.float64).reshape(3, 3)
+    Ts = np.stack([np.eye(4) * (i + 1) for i in range(3)])
+    k, t = LitFusionPointNet._batch_cameras(3, K, Ts)
+    assert k.shape == (3, 9) and k.dtype == np.float32 and k.flags.c_contiguous and np.array_equal(k[2], np.arange(9))
+    assert t.shape == (3, 16) and t.dtype == np.float32 and t[1, 0] == 2.0
+    k2, _ = LitFusionPointNet._batch_cameras(3, np.stack([K, K + 1, K + 2]), Ts)
+    assert np.array_equal(k2[1], np.arange(9) + 1)
 
 
 def test_sass_is_sm100a():
