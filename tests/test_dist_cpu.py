@@ -160,3 +160,29 @@ def test_sender_side_routing_equals_receiver_side_selection():
         mask = D.needed_by(flat, n_xyz, world, b)
         for rank in range(world):
             assert np.array_equal((mask >> rank) & 1, D.select_needed(flat, n_xyz, rank, world, b).astype(np.int64))
+
+
+def test_epoch_counter_counts_frames_of_batches():
+    """TileShardedFusion._frame_done(n): a 7-frame bnv_fuse_frames call counts as 7 frames towards the boundary-exchange
+    epoch (host logic only: the object is built without a device)."""
+    from bnv_fusion_b200.dist import TileShardedFusion
+    sh = TileShardedFusion.__new__(TileShardedFusion)
+    sh.world, sh.exchange_every, sh._since, sh.epochs = 4, 16, 0, 0
+
+    def fake_exchange():
+        sh._since = 0
+        sh.epochs += 1
+    sh.exchange_now = fake_exchange
+    for _ in range(2):
+        sh._frame_done(7)
+    assert (sh._since, sh.epochs) == (14, 0)
+    sh._frame_done(7)                       # 21 >= 16: one epoch, counter back to zero
+    assert (sh._since, sh.epochs) == (0, 1)
+    for _ in range(16):
+        sh._frame_done()
+    assert (sh._since, sh.epochs) == (0, 2)
+    sh.world = 1                            # a single GPU never exchanges
+    for _ in range(5):
+        sh._frame_done(7)
+    assert sh.epochs == 2
+
